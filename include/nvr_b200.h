@@ -1,0 +1,202 @@
+/* nvr_b200.h -- C-ABI of the B200-native instant-nvr per-ray hot path.
+ *
+ * The reference (zju3dv/instant-nvr @ a6f4d68) has no FFI for this path: it is PyTorch ops
+ * plus pytorch3d's KNN behind two Python seams,
+ *     Network.forward(wpts, viewdir, dists, batch)   lib/networks/bw_deform/inb_part_network_multiassign.py:126-168
+ *     Renderer.render(batch)                         lib/networks/renderer/inb_renderer.py:204-239
+ * The entry points below are what a ctypes binding for those two seams binds (INTEGRATION.md
+ * shows the stub); each cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *   - every pointer in NvrParams / NvrFrame and every array argument without the `_host` suffix is
+ *     a DEVICE pointer, fp32 row-major unless noted, BORROWED for the duration of the binding /
+ *     call (the caller -- PyTorch -- owns parameter and batch storage, so optimizers and
+ *     checkpoints keep working on the same memory).
+ *   - all work is enqueued on the caller's stream; no entry point synchronises the device except
+ *     the `_host` variants (which must, to hand back host results) and nvr_read_counters.
+ *   - return value: 0 = ok, non-zero = error; nvr_last_error(h) gives the message.  The library
+ *     never calls exit()/abort().
+ *   - one handle per device per host thread (thread-compatible, not thread-safe).
+ */
+#ifndef NVR_B200_H
+#define NVR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVR_ABI_VERSION 1
+#define NVR_MAX_LEVELS 16
+#define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
+#define NVR_NUM_JOINTS 24
+
+typedef struct NvrEngine* NvrHandle;
+
+/* One multi-resolution dense+hashed grid: lib/networks/embedders/part_base_embedder.py:13-104.
+ * `dense` = Embedder.dense (sum_l<start_hash res_l^3, F); `hash` = Embedder.hash (H, T, F);
+ * `bounds` = Embedder.bounds (2,3) -- read on the device at every launch, so the iter-1 bbox
+ * overwrite (:107-109) needs no re-binding.  res / size / dense_off are the host-side values of
+ * entries_num / entries_size (fp32) / entries_sum[l-1]. */
+typedef struct NvrGrid {
+    const float* dense;
+    const float* hash;
+    const float* bounds;
+    int32_t n_levels;
+    int32_t n_feat;
+    int32_t start_hash;
+    int32_t sum_features;          /* 1: per-level feature sum (part grids); 0: concat (deformer) */
+    int64_t table_size;            /* T = nextprime(2**log2_hashmap_size), :42 */
+    int32_t res[NVR_MAX_LEVELS];
+    float size[NVR_MAX_LEVELS];
+    int64_t dense_off[NVR_MAX_LEVELS];
+} NvrGrid;
+
+/* nn.Linear: weight (out, in) row-major, bias (out). */
+typedef struct NvrLinear {
+    const float* weight;
+    const float* bias;
+    int32_t in_dim;
+    int32_t out_dim;
+} NvrLinear;
+
+/* One part network: lib/networks/bw_deform/part_base_network.py:27-63. */
+typedef struct NvrPart {
+    NvrGrid grid;
+    NvrLinear occ[2];              /* 19 -> 64 -> 17 */
+    NvrLinear rgb[3];              /* 70 -> 64 [-> 64] -> 3 */
+    int32_t n_rgb;                 /* 2 (leg, arms) or 3 (body, head) linears */
+    int32_t n_latent;              /* rows of rgb_latent */
+    const float* rgb_latent;       /* (n_latent, 8) */
+} NvrPart;
+
+typedef struct NvrParams {
+    NvrPart part[NVR_NUM_PARTS];
+    NvrGrid deformer_grid;         /* lib/networks/deformers/uv_deformer.py:12-21 */
+    NvrLinear deformer_mlp[3];     /* 19 -> 32 -> 32 -> 3 */
+} NvrParams;
+
+/* Per-frame SMPL tensors, the `batch` keys the path consumes (produced by
+ * lib/datasets/h36m/tpose_dataset.py:454-600), without the leading batch dim of 1. */
+typedef struct NvrFrame {
+    const float* R;                /* (3,3)  world->pose rotation, blend_utils.py:366-382 */
+    const float* Th;               /* (3)    */
+    const float* pbw;              /* (D,H,W,C) blend-weight volume; channel C-1 = distance to SMPL */
+    int32_t pbw_dims[3];
+    int32_t pbw_channels;          /* 25 */
+    const float* pbounds;          /* (2,3) */
+    const float* part_pts;         /* (P, maxlen, 3) posed vertices per part */
+    const float* part_pbw;         /* (P, maxlen, 24) */
+    const int64_t* lengths2;       /* (P) valid vertices per part */
+    int32_t maxlen;
+    int32_t _pad0;
+    const float* A;                /* (24,4,4) T-pose -> posed */
+    const float* big_A;            /* (24,4,4) T-pose -> big pose */
+    const float* tuv;              /* (D',H',W',2) */
+    int32_t tuv_dims[3];
+    int32_t _pad1;
+    const float* tbounds;          /* (2,3) */
+    const float* frame_dim;        /* (1) f32 */
+    const int64_t* latent_index;   /* (1) int64 */
+} NvrFrame;
+
+typedef struct NvrConfig {
+    int32_t abi_version;           /* NVR_ABI_VERSION */
+    int32_t device;                /* CUDA device ordinal */
+    float smpl_thresh;             /* cfg.smpl_thresh */
+    int32_t mlp_mode;              /* 0: fp32 FFMA tiles (parity mode); 1: tcgen05 3xTF32 tensor-core tiles */
+} NvrConfig;
+
+/* Device-side work counters of the most recent pass (diagnostics / benchmark accounting). */
+typedef struct NvrCounters {
+    int64_t n_points;              /* samples submitted */
+    int64_t n_survivors;           /* samples with pnorm < smpl_thresh */
+    int64_t n_pairs[NVR_NUM_PARTS];/* flagged (sample, part) pairs */
+    int64_t kernel_launches;       /* kernels this handle has launched since creation */
+} NvrCounters;
+
+int nvr_abi_version(void);
+int nvr_create(const NvrConfig* cfg, NvrHandle* out);
+int nvr_destroy(NvrHandle h);
+const char* nvr_last_error(NvrHandle h);
+
+/* Borrow the nn.Parameter storages (Appendix D of SURVEY.md).  Cheap; call again whenever a
+ * storage moved (load_state_dict keeps storages, .cuda()/.to() do not). */
+int nvr_bind_params(NvrHandle h, const NvrParams* p);
+/* Borrow the per-frame tensors and run the per-frame preparation (distance-channel extraction,
+ * vertex packing) on `stream`. */
+int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream);
+
+/* Bytes of scratch needed to process up to `max_points` samples in one pass. */
+size_t nvr_workspace_bytes(NvrHandle h, int64_t max_points);
+
+/* == Network.forward, eval branch (inb_part_network_multiassign.py:126-168) ==
+ * wpts, viewdir (n,3) -> raw (n,4) = [r,g,b,occ], occ (n).  Samples are processed in passes of at
+ * most `ws_bytes`-worth of points. */
+int nvr_query_points(NvrHandle h, const float* wpts, const float* viewdir, int64_t n,
+                     float* raw, float* occ, void* workspace, size_t ws_bytes, void* stream);
+
+/* == Renderer.render, eval branch (inb_renderer.py:15-76,204-239 + net_utils.py:12-44) ==
+ * ray_o, ray_d (n_rays,3), near, far (n_rays) -> rgb_map (n_rays,3), acc_map (n_rays);
+ * raw (n_rays*n_samples,4) is written only when non-NULL (parity checks). */
+int nvr_render_rays(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_,
+                    const float* far_, int64_t n_rays, int32_t n_samples, float* rgb_map,
+                    float* acc_map, float* raw, void* workspace, size_t ws_bytes, void* stream);
+
+/* Same call with HOST ray buffers and HOST outputs (pinned memory recommended): copies the rays
+ * in, renders, copies rgb_map / acc_map back and synchronises `stream`.  `dev_io` is a device
+ * scratch of at least n_rays * 48 bytes. */
+int nvr_render_rays_host(NvrHandle h, const float* ray_o_host, const float* ray_d_host,
+                         const float* near_host, const float* far_host, int64_t n_rays,
+                         int32_t n_samples, float* rgb_map_host, float* acc_map_host, void* dev_io,
+                         void* workspace, size_t ws_bytes, void* stream);
+
+/* == Network.resd (inb_part_network_multiassign.py:122-124; uv_deformer.py:23-45, flag=None) ==
+ * canonical points (n,3) -> 0.05*tanh(MLP(grid(u,v,t))) (n,3). */
+int nvr_deformer_residual(NvrHandle h, const float* tpts, int64_t n, float* resd, void* stream);
+
+/* Grid embedding of one part (part_base_embedder.py:106-174): xyz (n,3) -> (n,19).  Exposed for
+ * per-stage parity tests and the gather roofline measurement. */
+int nvr_embed_part(NvrHandle h, int32_t part, const float* xyz, int64_t n, float* out, void* stream);
+
+/* Occ + rgb MLPs of one part on explicit inputs (part_base_network.py:50-60): emb (n, 20-float rows,
+ * 19 used), canonical view dirs (n,3) -> raw (n,4) = [rgb, occ].  Per-stage parity tests and the
+ * isolated MLP measurement.  Uses batch['latent_index'] of the bound frame. */
+int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const float* dirs, int64_t n, float* raw,
+                 void* workspace, size_t ws_bytes, void* stream);
+
+/* nvr_query_points plus per-stage taps for the parity tests: surv_of_sample (n) = survivor slot or -1,
+ * warp_dbg (n,5,8) = [flag, x, y, z, vx, vy, vz, pdist] of every (sample, part) after the warp stage.
+ * All n points must fit one pass. */
+int nvr_query_points_debug(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw,
+                           int32_t* surv_of_sample, float* warp_dbg, void* workspace, size_t ws_bytes, void* stream);
+
+/* Per-stage device timing.  nvr_profile(h, 1) clears the accumulators and makes every later launch
+ * record a CUDA-event pair on its stream; nvr_profile_read synchronises the device and sums them. */
+#define NVR_STAGE_PREP 0
+#define NVR_STAGE_CULL 1
+#define NVR_STAGE_WARP 2
+#define NVR_STAGE_EMBED 3     /* the grid gather */
+#define NVR_STAGE_MLP 4
+#define NVR_STAGE_RESOLVE 5
+#define NVR_NUM_STAGES 6
+typedef struct NvrStageProfile {
+    double ms[NVR_NUM_STAGES];            /* summed launch durations */
+    int64_t launches[NVR_NUM_STAGES];
+    int64_t passes;
+    int64_t survivors;                    /* summed over the profiled passes */
+    int64_t pairs[NVR_NUM_PARTS];
+} NvrStageProfile;
+int nvr_profile(NvrHandle h, int32_t enable);
+int nvr_profile_read(NvrHandle h, NvrStageProfile* out);
+
+/* Copies the device counters of the last pass to the host (synchronises `stream`). */
+int nvr_read_counters(NvrHandle h, NvrCounters* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVR_B200_H */

@@ -1,0 +1,456 @@
+// nvr_cabi.cu -- extern "C" surface of libnvr_b200.so (declared in include/nvr_b200.h).
+//
+// Host-side orchestration only: pointer bookkeeping, pass splitting, launches.  There is no CPU
+// compute path here; every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/nvr_b200.h"
+#include "nvr_kernels.cuh"
+
+struct NvrEngine {
+    NvrConfig cfg;
+    std::string err;
+    int sm_count = 148;
+    bool have_params = false, have_frame = false;
+    NvrParams params;
+    GridDev part_grid[NVR_PARTS];
+    GridDev def_grid;
+    PartMlpDev part_mlp[NVR_PARTS];
+    DeformerMlp def_mlp;
+    NvrFrame frame;
+    FrameDev fdev;
+    // per-frame device buffers owned by the engine (grow-only)
+    float* d_dist = nullptr; size_t dist_cap = 0;
+    float4* d_verts = nullptr; size_t verts_cap = 0;
+    int* d_part_off = nullptr;
+    int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
+    long long launches = 0;
+    long long last_points = 0;
+    // optional per-stage timing (nvr_profile): event pairs around every launch + per-pass counter snapshots
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int stage; size_t e0, e1; };
+    std::vector<Span> spans;
+    int* h_pass_counters = nullptr;         // pinned [PROF_MAX_PASSES][NVR_CTR_WORDS]
+    int n_pass_snap = 0;
+};
+static const int PROF_MAX_PASSES = 8192;
+
+struct StageTimer {                         // RAII: records an event pair on `st` when profiling is on
+    NvrEngine* h; cudaStream_t st; int stage; size_t e0 = 0; bool on;
+    StageTimer(NvrEngine* h_, cudaStream_t st_, int stage_) : h(h_), st(st_), stage(stage_), on(h_->profiling) {
+        if (!on) return;
+        if (h->ev_used + 2 > h->ev_pool.size()) {
+            for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+        }
+        e0 = h->ev_used; h->ev_used += 2;
+        cudaEventRecord(h->ev_pool[e0], st);
+    }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(h->ev_pool[e0 + 1], st);
+        h->spans.push_back({stage, e0, e0 + 1});
+    }
+};
+
+#define NVR_CHECK(h, expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                        \
+            return 2;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+static int fail(NvrEngine* h, const char* msg) {
+    if (h) h->err = msg;
+    return 1;
+}
+
+static GridDev to_dev(const NvrGrid& g) {
+    GridDev d;
+    memset(&d, 0, sizeof(d));
+    d.dense = g.dense; d.hash = g.hash; d.bounds = g.bounds;
+    d.n_levels = g.n_levels; d.n_feat = g.n_feat; d.start_hash = g.start_hash; d.sum_features = g.sum_features;
+    d.T = (unsigned long long)g.table_size;
+    d.T_magic = g.table_size > 1 ? (unsigned long long)((((unsigned __int128)1) << 64) / (unsigned __int128)g.table_size) : 0ull;
+    for (int l = 0; l < NVR_MAX_LEVELS; ++l) { d.res[l] = g.res[l]; d.size[l] = g.size[l]; d.dense_off[l] = g.dense_off[l]; }
+    return d;
+}
+static LinearDev to_dev(const NvrLinear& l) { return LinearDev{l.weight, l.bias, l.in_dim, l.out_dim}; }
+
+extern "C" int nvr_abi_version(void) { return NVR_ABI_VERSION; }
+
+extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
+    if (!cfg || !out) return 1;
+    *out = nullptr;
+    if (cfg->abi_version != NVR_ABI_VERSION) return 3;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return 4;                                        // no CUDA device: there is no CPU fallback
+    }
+    NvrEngine* h = new NvrEngine();
+    h->cfg = *cfg;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(cfg->device) != cudaSuccess || cudaMalloc(&h->d_part_off, 8 * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->d_counters_snapshot, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
+        cudaMemset(h->d_counters_snapshot, 0, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES) != cudaSuccess) {
+        cudaGetLastError();
+        delete h;
+        return 5;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int nvr_destroy(NvrHandle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_part_off); cudaFree(h->d_counters_snapshot);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
+    delete h;
+    return 0;
+}
+
+extern "C" const char* nvr_last_error(NvrHandle h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int nvr_bind_params(NvrHandle h, const NvrParams* p) {
+    if (!h || !p) return fail(h, "nvr_bind_params: null argument");
+    for (int i = 0; i < NVR_NUM_PARTS; ++i) {
+        const NvrPart& pt = p->part[i];
+        const NvrGrid& g = pt.grid;
+        if (g.n_levels < 1 || g.n_levels > NVR_MAX_LEVELS || g.n_feat != 16 || !g.sum_features || g.start_hash < 1)
+            return fail(h, "nvr_bind_params: part grid must be F=16, per-level feature sum, 1..16 levels, >=1 dense level");
+        if (pt.occ[0].in_dim != 19 || pt.occ[0].out_dim != 64 || pt.occ[1].in_dim != 64 || pt.occ[1].out_dim != 17)
+            return fail(h, "nvr_bind_params: occ MLP must be 19->64->17");
+        if (pt.n_rgb != 2 && pt.n_rgb != 3) return fail(h, "nvr_bind_params: rgb MLP must have 2 or 3 linears");
+        if (pt.rgb[0].in_dim != 70 || pt.rgb[0].out_dim != 64 || pt.rgb[pt.n_rgb - 1].in_dim != 64 ||
+            pt.rgb[pt.n_rgb - 1].out_dim != 3 || (pt.n_rgb == 3 && (pt.rgb[1].in_dim != 64 || pt.rgb[1].out_dim != 64)))
+            return fail(h, "nvr_bind_params: rgb MLP must be 70->64[->64]->3");
+        if (!g.dense || !g.hash || !g.bounds || !pt.rgb_latent) return fail(h, "nvr_bind_params: null table pointer");
+    }
+    const NvrGrid& dg = p->deformer_grid;
+    if (dg.n_feat != 2 || dg.sum_features || dg.n_levels != 8 || dg.start_hash < 1)
+        return fail(h, "nvr_bind_params: deformer grid must be 8 levels x F=2, concat");
+    if (p->deformer_mlp[0].in_dim != 19 || p->deformer_mlp[0].out_dim != 32 || p->deformer_mlp[1].in_dim != 32 ||
+        p->deformer_mlp[1].out_dim != 32 || p->deformer_mlp[2].in_dim != 32 || p->deformer_mlp[2].out_dim != 3)
+        return fail(h, "nvr_bind_params: deformer MLP must be 19->32->32->3");
+    h->params = *p;
+    for (int i = 0; i < NVR_NUM_PARTS; ++i) {
+        const NvrPart& pt = p->part[i];
+        h->part_grid[i] = to_dev(pt.grid);
+        PartMlpDev& m = h->part_mlp[i];
+        m.occ[0] = to_dev(pt.occ[0]); m.occ[1] = to_dev(pt.occ[1]);
+        for (int k = 0; k < 3; ++k) m.rgb[k] = to_dev(pt.rgb[k < pt.n_rgb ? k : 0]);
+        m.n_rgb = pt.n_rgb; m.n_latent = pt.n_latent; m.latent = pt.rgb_latent;
+    }
+    h->def_grid = to_dev(dg);
+    h->def_mlp = DeformerMlp{p->deformer_mlp[0].weight, p->deformer_mlp[0].bias, p->deformer_mlp[1].weight,
+                             p->deformer_mlp[1].bias, p->deformer_mlp[2].weight, p->deformer_mlp[2].bias};
+    h->have_params = true;
+    return 0;
+}
+
+extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
+    if (!h || !f) return fail(h, "nvr_bind_frame: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!f->R || !f->Th || !f->pbw || !f->pbounds || !f->part_pts || !f->part_pbw || !f->lengths2 || !f->A ||
+        !f->big_A || !f->tuv || !f->tbounds || !f->frame_dim || !f->latent_index)
+        return fail(h, "nvr_bind_frame: null tensor pointer");
+    if (f->pbw_channels < 1 || f->maxlen < 1) return fail(h, "nvr_bind_frame: bad pbw_channels / maxlen");
+    for (int a = 0; a < 3; ++a)
+        if (f->pbw_dims[a] < 1 || f->tuv_dims[a] < 1) return fail(h, "nvr_bind_frame: bad volume dims");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    const size_t n_vox = (size_t)f->pbw_dims[0] * f->pbw_dims[1] * f->pbw_dims[2];
+    const size_t n_verts = (size_t)NVR_NUM_PARTS * f->maxlen;
+    if (n_vox > h->dist_cap) {
+        NVR_CHECK(h, cudaFree(h->d_dist));
+        h->d_dist = nullptr; h->dist_cap = 0;
+        NVR_CHECK(h, cudaMalloc(&h->d_dist, n_vox * sizeof(float)));
+        h->dist_cap = n_vox;
+    }
+    if (n_verts > h->verts_cap) {
+        NVR_CHECK(h, cudaFree(h->d_verts));
+        h->d_verts = nullptr; h->verts_cap = 0;
+        NVR_CHECK(h, cudaMalloc(&h->d_verts, n_verts * sizeof(float4)));
+        h->verts_cap = n_verts;
+    }
+    StageTimer tm_(h, stream, NVR_STAGE_PREP);
+    k_frame_prep<<<std::min<int>(h->sm_count * 4, (int)((std::max(n_vox, n_verts) + 255) / 256)), 256, 0, stream>>>(
+        f->pbw, (int)n_vox, f->pbw_channels, h->d_dist, f->part_pts, (const long long*)f->lengths2, f->maxlen,
+        h->d_verts, h->d_part_off);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    h->frame = *f;
+    FrameDev& d = h->fdev;
+    d.R = f->R; d.Th = f->Th;
+    d.dist = VolumeDev{h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], 1, f->pbounds};
+    d.tuv = VolumeDev{f->tuv, f->tuv_dims[0], f->tuv_dims[1], f->tuv_dims[2], 2, f->tbounds};
+    d.verts = h->d_verts; d.part_off = h->d_part_off; d.part_pbw = f->part_pbw; d.maxlen = f->maxlen;
+    d.A = f->A; d.bigA = f->big_A; d.frame_dim = f->frame_dim; d.latent_index = (const long long*)f->latent_index;
+    h->have_frame = true;
+    return 0;
+}
+
+// ---- workspace ---------------------------------------------------------------------------
+static const size_t WS_HEADER = 256;
+static const size_t WS_PER_POINT = sizeof(int) + sizeof(float4) + NVR_NUM_PARTS * sizeof(PairRec) +
+                                   NVR_NUM_PARTS * NVR_EMB_STRIDE * sizeof(float) + NVR_NUM_PARTS * sizeof(float4);
+
+extern "C" size_t nvr_workspace_bytes(NvrHandle, int64_t max_points) {
+    if (max_points < 1) max_points = 1;
+    const size_t pts = ((size_t)max_points + 63) & ~(size_t)63;
+    return WS_HEADER + (pts + 64) * WS_PER_POINT;
+}
+
+struct Workspace {
+    int* counters; int* surv_of_sample; float4* surv; PairRec* pairs; float* emb; float4* raws;
+    long long cap;
+};
+static bool carve(void* ws, size_t bytes, Workspace& w) {
+    if (!ws || bytes < WS_HEADER + 65 * WS_PER_POINT || ((uintptr_t)ws & 255)) return false;
+    long long cap = (long long)((bytes - WS_HEADER) / WS_PER_POINT) - 64;
+    cap = std::min<long long>(cap & ~63ll, 1ll << 30);
+    if (cap < 64) return false;
+    char* p = (char*)ws;
+    w.counters = (int*)p; p += WS_HEADER;
+    w.surv = (float4*)p; p += cap * sizeof(float4);
+    w.pairs = (PairRec*)p; p += cap * NVR_NUM_PARTS * sizeof(PairRec);
+    w.raws = (float4*)p; p += cap * NVR_NUM_PARTS * sizeof(float4);
+    w.emb = (float*)p; p += cap * NVR_NUM_PARTS * NVR_EMB_STRIDE * sizeof(float);
+    w.surv_of_sample = (int*)p;
+    w.cap = cap;
+    return true;
+}
+
+static int grid_for(long long items, int per_block, int max_blocks) {
+    long long b = (items + per_block - 1) / per_block;
+    return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
+}
+
+// One pass over `n` samples (n <= ws.cap): cull -> warp -> 5x(embed, mlp).  The caller resolves.
+static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const float* ray_d, const float* near_,
+                    const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
+                    float* dbg = nullptr) {
+    const int sm = h->sm_count;
+    NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
+    { StageTimer t(h, st, NVR_STAGE_CULL);
+    k_cull<<<grid_for(n, 256, sm * 16), 256, 0, st>>>(h->fdev, pts, ray_d, near_, far_, n, n_samples, h->cfg.smpl_thresh,
+                                                      w.counters, w.surv_of_sample, w.surv); }
+    { StageTimer t(h, st, NVR_STAGE_WARP);
+    k_warp<<<grid_for(n, 128, sm * 8), 128, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, h->cfg.smpl_thresh,
+                                                     w.counters, w.surv, w.pairs, (int)w.cap, w.raws, dbg); }
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) {
+        const PairRec* pl = w.pairs + (long long)p * w.cap;
+        float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
+        { StageTimer t(h, st, NVR_STAGE_EMBED);
+        k_embed<<<grid_for(n, 64, sm * 8), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
+                                                         el, NVR_EMB_STRIDE); }
+        StageTimer t(h, st, NVR_STAGE_MLP);
+        k_mlp<<<grid_for(n, MLP_TILE, sm), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[p], p, h->fdev.latent_index,
+                                                                      w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
+    }
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches += 2 + 2 * NVR_NUM_PARTS;
+    h->last_points = n;
+    return 0;
+}
+
+static int snapshot_counters(NvrEngine* h, const Workspace& w, cudaStream_t st) {
+    if (h->profiling && h->n_pass_snap < PROF_MAX_PASSES) {
+        NVR_CHECK(h, cudaMemcpyAsync(h->h_pass_counters + (size_t)h->n_pass_snap * NVR_CTR_WORDS, w.counters,
+                                     NVR_CTR_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
+        h->n_pass_snap++;
+    }
+    NVR_CHECK(h, cudaMemcpyAsync(h->d_counters_snapshot, w.counters, NVR_CTR_WORDS * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+static int ready(NvrEngine* h, const char* who) {
+    if (!h) return 1;
+    if (!h->have_params || !h->have_frame) {
+        h->err = std::string(who) + ": bind_params and bind_frame first";
+        return 1;
+    }
+    cudaError_t e = cudaSetDevice(h->cfg.device);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return 2; }
+    return 0;
+}
+
+extern "C" int nvr_query_points(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw, float* occ,
+                                void* workspace, size_t ws_bytes, void* stream_) {
+    if (int rc = ready(h, "nvr_query_points")) return rc;
+    if (n < 0 || (n > 0 && (!wpts || !viewdir || !raw))) return fail(h, "nvr_query_points: null argument");
+    Workspace w;
+    if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_query_points: workspace too small or not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream_;
+    for (long long s = 0; s < n; s += w.cap) {
+        const long long m = std::min<long long>(w.cap, n - s);
+        if (int rc = run_pass(h, w, wpts + s * 3, nullptr, nullptr, nullptr, m, 0, viewdir + s * 3, 1, st)) return rc;
+        { StageTimer t(h, st, NVR_STAGE_RESOLVE);
+        k_resolve_points<<<grid_for(m, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, m, (float4*)raw + s,
+                                                                           occ ? occ + s : nullptr); }
+        NVR_CHECK(h, cudaGetLastError());
+        h->launches++;
+        if (int rc = snapshot_counters(h, w, st)) return rc;
+    }
+    return 0;
+}
+
+extern "C" int nvr_render_rays(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                               int64_t n_rays, int32_t n_samples, float* rgb_map, float* acc_map, float* raw,
+                               void* workspace, size_t ws_bytes, void* stream_) {
+    if (int rc = ready(h, "nvr_render_rays")) return rc;
+    if (n_rays < 0 || n_samples < 1) return fail(h, "nvr_render_rays: bad n_rays / n_samples");
+    if (n_rays > 0 && (!ray_o || !ray_d || !near_ || !far_ || !rgb_map || !acc_map)) return fail(h, "nvr_render_rays: null argument");
+    Workspace w;
+    if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_render_rays: workspace too small or not 256-byte aligned");
+    const long long rays_per_pass = w.cap / n_samples;
+    if (rays_per_pass < 1) return fail(h, "nvr_render_rays: workspace smaller than one ray");
+    cudaStream_t st = (cudaStream_t)stream_;
+    for (long long r = 0; r < n_rays; r += rays_per_pass) {
+        const long long nr = std::min<long long>(rays_per_pass, n_rays - r);
+        const long long m = nr * n_samples;
+        if (int rc = run_pass(h, w, ray_o + r * 3, ray_d + r * 3, near_ + r, far_ + r, m, n_samples, ray_d + r * 3, n_samples, st))
+            return rc;
+        { StageTimer t(h, st, NVR_STAGE_RESOLVE);
+        k_resolve_rays<<<grid_for(nr, 8, h->sm_count * 8), 256, 0, st>>>(w.surv_of_sample, w.raws, nr, n_samples, rgb_map + r * 3,
+                                                                       acc_map + r, raw ? (float4*)raw + r * n_samples : nullptr); }
+        NVR_CHECK(h, cudaGetLastError());
+        h->launches++;
+        if (int rc = snapshot_counters(h, w, st)) return rc;
+    }
+    return 0;
+}
+
+extern "C" int nvr_render_rays_host(NvrHandle h, const float* ray_o_host, const float* ray_d_host, const float* near_host,
+                                    const float* far_host, int64_t n_rays, int32_t n_samples, float* rgb_map_host,
+                                    float* acc_map_host, void* dev_io, void* workspace, size_t ws_bytes, void* stream_) {
+    if (int rc = ready(h, "nvr_render_rays_host")) return rc;
+    if (!dev_io || !ray_o_host || !ray_d_host || !near_host || !far_host || !rgb_map_host || !acc_map_host)
+        return fail(h, "nvr_render_rays_host: null argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    float* d = (float*)dev_io;                      // [o 3n | d 3n | near n | far n | rgb 3n | acc n] = 12n floats
+    float *d_o = d, *d_d = d + 3 * n_rays, *d_n = d + 6 * n_rays, *d_f = d + 7 * n_rays, *d_rgb = d + 8 * n_rays,
+          *d_acc = d + 11 * n_rays;
+    NVR_CHECK(h, cudaMemcpyAsync(d_o, ray_o_host, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    NVR_CHECK(h, cudaMemcpyAsync(d_d, ray_d_host, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    NVR_CHECK(h, cudaMemcpyAsync(d_n, near_host, n_rays * sizeof(float), cudaMemcpyHostToDevice, st));
+    NVR_CHECK(h, cudaMemcpyAsync(d_f, far_host, n_rays * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = nvr_render_rays(h, d_o, d_d, d_n, d_f, n_rays, n_samples, d_rgb, d_acc, nullptr, workspace, ws_bytes, stream_))
+        return rc;
+    NVR_CHECK(h, cudaMemcpyAsync(rgb_map_host, d_rgb, n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NVR_CHECK(h, cudaMemcpyAsync(acc_map_host, d_acc, n_rays * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NVR_CHECK(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int nvr_deformer_residual(NvrHandle h, const float* tpts, int64_t n, float* resd, void* stream_) {
+    if (int rc = ready(h, "nvr_deformer_residual")) return rc;
+    if (n > 0 && (!tpts || !resd)) return fail(h, "nvr_deformer_residual: null argument");
+    if (n == 0) return 0;
+    k_deformer<<<grid_for(n, 128, h->sm_count * 8), 128, 0, (cudaStream_t)stream_>>>(h->fdev, h->def_grid, h->def_mlp, tpts, n, resd);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" int nvr_embed_part(NvrHandle h, int32_t part, const float* xyz, int64_t n, float* out, void* stream_) {
+    if (!h || !h->have_params) return fail(h, "nvr_embed_part: bind_params first");
+    if (part < 0 || part >= NVR_NUM_PARTS) return fail(h, "nvr_embed_part: bad part");
+    if (n > 0 && (!xyz || !out)) return fail(h, "nvr_embed_part: null argument");
+    if (n == 0) return 0;
+    if (n >= (1ll << 31)) return fail(h, "nvr_embed_part: n must be < 2^31");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    k_embed<<<grid_for(n, 64, h->sm_count * 8), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const float* dirs, int64_t n, float* raw,
+                            void* workspace, size_t ws_bytes, void* stream_) {
+    if (int rc = ready(h, "nvr_part_mlp")) return rc;
+    if (part < 0 || part >= NVR_NUM_PARTS) return fail(h, "nvr_part_mlp: bad part");
+    if (n > 0 && (!emb || !dirs || !raw)) return fail(h, "nvr_part_mlp: null argument");
+    if (n == 0) return 0;
+    Workspace w;
+    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_part_mlp: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream_;
+    k_make_pairs<<<(int)((n + 255) / 256), 256, 0, st>>>(dirs, (int)n, w.pairs, w.counters);
+    k_mlp<<<grid_for(n, MLP_TILE, h->sm_count), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[part], 0, h->fdev.latent_index, w.counters,
+                                                                          w.pairs, emb, (float4*)raw, 1);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches += 2;
+    return 0;
+}
+
+extern "C" int nvr_query_points_debug(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw,
+                                      int32_t* surv_of_sample, float* warp_dbg, void* workspace, size_t ws_bytes, void* stream_) {
+    if (int rc = ready(h, "nvr_query_points_debug")) return rc;
+    Workspace w;
+    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_query_points_debug: workspace must hold all points in one pass");
+    if (!wpts || !viewdir || !raw || !surv_of_sample || !warp_dbg) return fail(h, "nvr_query_points_debug: null argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    NVR_CHECK(h, cudaMemsetAsync(warp_dbg, 0, (size_t)n * NVR_NUM_PARTS * 8 * sizeof(float), st));
+    if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, warp_dbg)) return rc;
+    k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, n, (float4*)raw, nullptr);
+    NVR_CHECK(h, cudaMemcpyAsync(surv_of_sample, w.surv_of_sample, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return snapshot_counters(h, w, st);
+}
+
+extern "C" int nvr_profile(NvrHandle h, int32_t enable) {
+    if (!h) return 1;
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    if (enable && !h->h_pass_counters)
+        NVR_CHECK(h, cudaMallocHost(&h->h_pass_counters, (size_t)PROF_MAX_PASSES * NVR_CTR_WORDS * sizeof(int)));
+    h->profiling = enable != 0;
+    h->ev_used = 0; h->spans.clear(); h->n_pass_snap = 0;
+    return 0;
+}
+
+extern "C" int nvr_profile_read(NvrHandle h, NvrStageProfile* out) {
+    if (!h || !out) return fail(h, "nvr_profile_read: null argument");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    NVR_CHECK(h, cudaDeviceSynchronize());
+    memset(out, 0, sizeof(*out));
+    for (const auto& sp : h->spans) {
+        float ms = 0.f;
+        NVR_CHECK(h, cudaEventElapsedTime(&ms, h->ev_pool[sp.e0], h->ev_pool[sp.e1]));
+        out->ms[sp.stage] += ms;
+        out->launches[sp.stage]++;
+    }
+    out->passes = h->n_pass_snap;
+    for (int i = 0; i < h->n_pass_snap; ++i) {
+        const int* c = h->h_pass_counters + (size_t)i * NVR_CTR_WORDS;
+        out->survivors += c[NVR_CTR_SURV];
+        for (int p = 0; p < NVR_NUM_PARTS; ++p) out->pairs[p] += c[NVR_CTR_PAIR + p];
+    }
+    return 0;
+}
+
+extern "C" int nvr_read_counters(NvrHandle h, NvrCounters* out, void* stream_) {
+    if (!h || !out) return fail(h, "nvr_read_counters: null argument");
+    int host[NVR_CTR_WORDS];
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    NVR_CHECK(h, cudaMemcpyAsync(host, h->d_counters_snapshot, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    NVR_CHECK(h, cudaStreamSynchronize((cudaStream_t)stream_));
+    out->n_points = h->last_points;
+    out->n_survivors = host[NVR_CTR_SURV];
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) out->n_pairs[p] = host[NVR_CTR_PAIR + p];
+    out->kernel_launches = h->launches;
+    return 0;
+}

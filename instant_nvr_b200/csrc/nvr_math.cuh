@@ -1,0 +1,384 @@
+// nvr_math.cuh -- per-sample arithmetic of the hot path, shared by every kernel.
+//
+// Everything here is `__host__ __device__` so the exact same statements can be compiled with g++
+// by tests/host_emul (a TEST-ONLY harness that checks this arithmetic against the oracle without
+// a GPU).  The product never runs it on the CPU: the kernels in nvr_kernels.cu are the only callers
+// in libnvr_b200.so.
+//
+// Reference citations are to zju3dv/instant-nvr @ a6f4d68.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define NVR_HD __host__ __device__ __forceinline__
+#else
+#define NVR_HD inline
+struct float4 { float x, y, z, w; };      // host emulation only
+#endif
+
+#define NVR_LEVELS 16
+#define NVR_PARTS 5
+#define NVR_JOINTS 24
+#define NVR_KNN 4
+
+// Device-side view of one grid (mirrors NvrGrid, plus the Barrett constant for `% T`).
+struct GridDev {
+    const float* dense;
+    const float* hash;
+    const float* bounds;
+    int n_levels, n_feat, start_hash, sum_features;
+    unsigned long long T;
+    unsigned long long T_magic;   // floor(2^64 / T)
+    int res[NVR_LEVELS];
+    float size[NVR_LEVELS];
+    long long dense_off[NVR_LEVELS];
+};
+
+struct VolumeDev {                // a (D,H,W,C) fp32 volume indexed by the point's (x,y,z)
+    const float* data;
+    int D, H, W, C;
+    const float* bounds;          // (2,3) device
+};
+
+NVR_HD float nvr_softplus(float x) {          // torch.nn.Softplus(beta=1, threshold=20)
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+NVR_HD float nvr_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------
+// hash-grid index arithmetic                          part_base_embedder.py:112-136, 158-159
+// ---------------------------------------------------------------------------------------
+NVR_HD unsigned long long nvr_umulhi64(unsigned long long a, unsigned long long b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// h mod T for h < 2^63 via Barrett reduction (T is one of four primes, never a power of two)
+NVR_HD unsigned long long nvr_mod_T(unsigned long long h, unsigned long long T, unsigned long long magic) {
+    unsigned long long q = nvr_umulhi64(h, magic);
+    unsigned long long r = h - q * T;
+    return r >= T ? r - T : r;
+}
+
+struct LevelCoord {
+    int i0[3], i1[3];   // clamped integer corner coordinates for offset 0 / 1 along each axis
+    float o[3];         // f - float(i0): trilinear offset measured from the CLAMPED corner (:118)
+};
+
+// u: normalised coordinate (xyz - b0) / (b1 - b0), NOT clamped (:112)
+NVR_HD void nvr_level_coord(const float u[3], float size, int res, LevelCoord& lc) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float f = u[a] / size;                               // :115  (IEEE fp32 divide)
+        long long t0 = (long long)(f + 0.0f);                // :116  .long() truncates toward zero
+        long long t1 = (long long)(f + 1.0f);
+        long long hi = (long long)res - 1;
+        t0 = t0 < 0 ? 0 : (t0 > hi ? hi : t0);               // :117
+        t1 = t1 < 0 ? 0 : (t1 > hi ? hi : t1);
+        lc.i0[a] = (int)t0;
+        lc.i1[a] = (int)t1;
+        lc.o[a] = f - (float)t0;                             // :118
+    }
+}
+
+// corner c: x = bit 2, y = bit 1, z = bit 0 (offsets table, :81-88)
+NVR_HD float nvr_corner_weight(const LevelCoord& lc, int c) {
+    float wx = (c & 4) ? lc.o[0] : 1.0f - lc.o[0];           // (1-off) + (2*off-1)*o  (:158)
+    float wy = (c & 2) ? lc.o[1] : 1.0f - lc.o[1];
+    float wz = (c & 1) ? lc.o[2] : 1.0f - lc.o[2];
+    return (wx * wy) * wz;                                   // :159
+}
+
+// Row of corner c of level l inside `dense` (l < start_hash) or `hash` flattened to (H*T, F).
+NVR_HD long long nvr_corner_row(const GridDev& g, int l, const LevelCoord& lc, int c) {
+    long long ix = (c & 4) ? lc.i1[0] : lc.i0[0];
+    long long iy = (c & 2) ? lc.i1[1] : lc.i0[1];
+    long long iz = (c & 1) ? lc.i1[2] : lc.i0[2];
+    if (l < g.start_hash) {
+        long long r = g.res[l];
+        return ix * r * r + iy * r + iz + g.dense_off[l];    // :124-129
+    }
+    unsigned long long h = ((unsigned long long)ix * 1ull) ^ ((unsigned long long)iy * 19349663ull) ^
+                           ((unsigned long long)iz * 83492791ull);          // :132-135 (int64, no wrap)
+    return (long long)(nvr_mod_T(h, g.T, g.T_magic) + (unsigned long long)(l - g.start_hash) * g.T);   // :136
+}
+
+NVR_HD const float* nvr_level_table(const GridDev& g, int l) { return l < g.start_hash ? g.dense : g.hash; }
+
+NVR_HD void nvr_normalise(const GridDev& g, const float x[3], float u[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) u[a] = (x[a] - g.bounds[a]) / (g.bounds[3 + a] - g.bounds[a]);   // :112
+}
+
+// Scalar (one thread = one point) embedding with F features per entry.  Used by the deformer (F=2,
+// concat) and by the host emulation; the part grids' production path is the quad-lane gather kernel,
+// which shares nvr_level_coord / nvr_corner_row / nvr_corner_weight with this function.
+//   sum_features: out[3 + l] = sum_f sum_c w_c * t[row_c][f];  concat: out[3 + l*F + f]
+template <int F>
+NVR_HD void nvr_embed_point(const GridDev& g, const float x[3], float* out) {
+    float u[3];
+    nvr_normalise(g, x, u);
+    out[0] = u[0]; out[1] = u[1]; out[2] = u[2];
+    for (int l = 0; l < g.n_levels; ++l) {
+        LevelCoord lc;
+        nvr_level_coord(u, g.size[l], g.res[l], lc);
+        const float* tab = nvr_level_table(g, l);
+        float acc[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float w = nvr_corner_weight(lc, c);
+            const float* row = tab + nvr_corner_row(g, l, lc, c) * F;
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[f] += w * row[f];                   // :160
+        }
+        if (g.sum_features) {
+            float s = 0.0f;
+#pragma unroll
+            for (int f = 0; f < F; ++f) s += acc[f];                            // :165
+            out[3 + l] = s;
+        } else {
+#pragma unroll
+            for (int f = 0; f < F; ++f) out[3 + l * F + f] = acc[f];            // :169
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// trilinear volume lookup == F.grid_sample(bilinear, border, align_corners=True)
+//                                                     blend_utils.py:501-525, 528-555
+// ---------------------------------------------------------------------------------------
+// channels [ch0, ch0+nch) of the C-channel volume; point axis x->D, y->H, z->W.
+NVR_HD void nvr_sample_volume(const VolumeDev& v, const float p[3], int ch0, int nch, float* out) {
+    const int dims[3] = {v.D, v.H, v.W};
+    float c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float g = (p[a] - v.bounds[a]) / (v.bounds[3 + a] - v.bounds[a]);
+        g = g * 2.0f - 1.0f;
+        float t = ((g + 1.0f) / 2.0f) * (float)(dims[a] - 1);     // grid_sampler_unnormalize, align_corners
+        t = fminf(fmaxf(t, 0.0f), (float)(dims[a] - 1));          // clip_coordinates (border)
+        c[a] = t;
+    }
+    // ATen names: x <-> W (our z), y <-> H (our y), z <-> D (our x)
+    const float ix = c[2], iy = c[1], iz = c[0];
+    const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
+    const float x1 = x0 + 1.0f, y1 = y0 + 1.0f, z1 = z0 + 1.0f;
+    for (int k = 0; k < nch; ++k) out[k] = 0.0f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {                       // tnw, tne, tsw, tse, bnw, bne, bsw, bse
+        const bool hx = n & 1, hy = n & 2, hz = n & 4;
+        const float wx = hx ? (ix - x0) : (x1 - ix);
+        const float wy = hy ? (iy - y0) : (y1 - iy);
+        const float wz = hz ? (iz - z0) : (z1 - iz);
+        const float w = (wx * wy) * wz;
+        const int cx = (int)(hx ? x1 : x0), cy = (int)(hy ? y1 : y0), cz = (int)(hz ? z1 : z0);
+        if (cx <= v.W - 1 && cy <= v.H - 1 && cz <= v.D - 1) {    // within_bounds_3d (>= 0 holds after the clip)
+            const float* src = v.data + (((long long)cz * v.H + cy) * v.W + cx) * v.C + ch0;
+            for (int k = 0; k < nch; ++k) out[k] += src[k] * w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K=4 nearest vertices -> Gaussian blend weights                 blend_utils.py:732-763
+// ---------------------------------------------------------------------------------------
+struct Knn4 {
+    float d2[NVR_KNN];      // ascending
+    int idx[NVR_KNN];
+};
+NVR_HD void nvr_knn_init(Knn4& k) {
+#pragma unroll
+    for (int i = 0; i < NVR_KNN; ++i) { k.d2[i] = INFINITY; k.idx[i] = 0; }
+}
+// insert keeping ascending order; ties keep the earlier index first (what a stable top-k does)
+NVR_HD void nvr_knn_insert(Knn4& k, float d2, int j) {
+    if (d2 < k.d2[3]) {
+        if (d2 < k.d2[2]) {
+            k.d2[3] = k.d2[2]; k.idx[3] = k.idx[2];
+            if (d2 < k.d2[1]) {
+                k.d2[2] = k.d2[1]; k.idx[2] = k.idx[1];
+                if (d2 < k.d2[0]) {
+                    k.d2[1] = k.d2[0]; k.idx[1] = k.idx[0];
+                    k.d2[0] = d2; k.idx[0] = j;
+                } else { k.d2[1] = d2; k.idx[1] = j; }
+            } else { k.d2[2] = d2; k.idx[2] = j; }
+        } else { k.d2[3] = d2; k.idx[3] = j; }
+    }
+}
+
+// verts: packed float4 (x,y,z,_) of ONE part, `count` of them.  Exact brute force.
+NVR_HD void nvr_knn_scan(const float4* verts, int count, const float p[3], Knn4& k) {
+    for (int j = 0; j < count; ++j) {
+#ifdef __CUDA_ARCH__
+        const float4 v = __ldg(verts + j);
+#else
+        const float4 v = verts[j];
+#endif
+        const float dx = p[0] - v.x, dy = p[1] - v.y, dz = p[2] - v.z;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        nvr_knn_insert(k, d2, j);
+    }
+}
+
+// From the 4 neighbours to (bw[24], pdist): sample_blend_closest_points, :741-763.
+// pbw_part: (maxlen, 24) rows of this part.  n_valid < 4 only if the part has < 4 vertices.
+NVR_HD float nvr_knn_blend(const Knn4& k, const float* pbw_part, float bw[NVR_JOINTS]) {
+    float d[NVR_KNN], w[NVR_KNN], wsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVR_KNN; ++i) {
+        d[i] = sqrtf(k.d2[i]);                                   // cast_knn_points :736
+        w[i] = expf(-(d[i] * d[i]) / 0.01125f);                  // :746, 2*radius^2 = 2*0.075^2
+        wsum += w[i];
+    }
+    const float denom = wsum + 1e-8f;                            // :747
+    float pdist = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVR_KNN; ++i) {
+        w[i] = w[i] / denom;
+        pdist += d[i] * w[i];                                    // :748
+    }
+#pragma unroll
+    for (int j = 0; j < NVR_JOINTS; ++j) bw[j] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVR_KNN; ++i) {
+        const float* row = pbw_part + (long long)k.idx[i] * NVR_JOINTS;
+#pragma unroll
+        for (int j = 0; j < NVR_JOINTS; ++j) bw[j] += row[j] * w[i];   // :762
+    }
+    return pdist;
+}
+
+// ---------------------------------------------------------------------------------------
+// LBS: pose space -> T pose -> big pose             blend_utils.py:293-317, 395-487
+// ---------------------------------------------------------------------------------------
+// A, bigA: (24,4,4) row-major.  In: pose-space point p, direction d, blend weights bw.
+// Out: big-pose point x0 and direction v.
+NVR_HD void nvr_lbs_to_bigpose(const float bw[NVR_JOINTS], const float* A, const float* bigA,
+                               const float p[3], const float d[3], float x0[3], float v[3]) {
+    float M[12], B[12];                                           // rows 0..2 of the blended 4x4s
+#pragma unroll
+    for (int e = 0; e < 12; ++e) { M[e] = 0.0f; B[e] = 0.0f; }
+#pragma unroll
+    for (int j = 0; j < NVR_JOINTS; ++j) {
+        const float w = bw[j];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            M[e] += w * A[j * 16 + e];                            // get_inverse_blend_params :415
+            B[e] += w * bigA[j * 16 + e];                         // get_blend_params :402
+        }
+    }
+    // 3x3 inverse by transposed cofactors / (det + fp32 eps)      torch_inverse_3x3 :293-317
+    const float a = M[0], b = M[1], c = M[2], dd = M[4], e = M[5], f = M[6], g = M[8], h = M[9], i = M[10];
+    const float m00 = e * i - f * h, m01 = dd * i - f * g, m02 = dd * h - e * g;
+    const float m10 = b * i - c * h, m11 = a * i - c * g, m12 = a * h - b * g;
+    const float m20 = b * f - c * e, m21 = a * f - c * dd, m22 = a * e - b * dd;
+    const float det = (a * m00 - b * m01) + c * m02;
+    const float den = det + 1.1920928955078125e-07f;
+    float Ri[9];
+    Ri[0] = m00 / den;  Ri[1] = -m10 / den; Ri[2] = m20 / den;
+    Ri[3] = -m01 / den; Ri[4] = m11 / den;  Ri[5] = -m21 / den;
+    Ri[6] = m02 / den;  Ri[7] = -m12 / den; Ri[8] = m22 / den;
+    const float q[3] = {p[0] - M[3], p[1] - M[7], p[2] - M[11]};  // pose_points_to_tpose_points :433
+    float t[3], td[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        t[r] = (Ri[r * 3 + 0] * q[0] + Ri[r * 3 + 1] * q[1]) + Ri[r * 3 + 2] * q[2];      // :436
+        td[r] = (Ri[r * 3 + 0] * d[0] + Ri[r * 3 + 1] * d[1]) + Ri[r * 3 + 2] * d[2];     // :453
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        x0[r] = ((B[r * 4 + 0] * t[0] + B[r * 4 + 1] * t[1]) + B[r * 4 + 2] * t[2]) + B[r * 4 + 3];   // :469-470
+        v[r] = (B[r * 4 + 0] * td[0] + B[r * 4 + 1] * td[1]) + B[r * 4 + 2] * td[2];                  // :486
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// view-direction encoding                                       freq_embedder.py:20-31
+// ---------------------------------------------------------------------------------------
+NVR_HD void nvr_posenc27(const float v[3], float* out) {
+    out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float fr = (float)(1 << k);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float x = v[a] * fr;
+            out[3 + k * 6 + a] = sinf(x);
+            out[3 + k * 6 + 3 + a] = cosf(x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// UV-time deformer                                              uv_deformer.py:23-45
+// ---------------------------------------------------------------------------------------
+// Weights are read through plain pointers (global or shared memory; row-major (out,in)).
+struct DeformerMlp {
+    const float *w0, *b0, *w1, *b1, *w2, *b2;    // 32x19, 32, 32x32, 32, 3x32, 3
+};
+
+NVR_HD void nvr_deformer_point(const GridDev& g, const DeformerMlp& m, const VolumeDev& tuv, float frame_dim,
+                               const float x0[3], float resd[3]) {
+    float uvt[3];
+    nvr_sample_volume(tuv, x0, 0, 2, uvt);                        // pts_sample_uv :32
+    uvt[2] = frame_dim;                                           // :35
+    float e[19];
+    nvr_embed_point<2>(g, uvt, e);                                // :37 (8 levels x 2 features, concat)
+    float h1[32], h2[32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        float acc = m.b0[o];
+#pragma unroll
+        for (int i = 0; i < 19; ++i) acc += m.w0[o * 19 + i] * e[i];
+        h1[o] = nvr_softplus(acc);
+    }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        float acc = m.b1[o];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += m.w1[o * 32 + i] * h1[i];
+        h2[o] = nvr_softplus(acc);
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        float acc = m.b2[o];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += m.w2[o * 32 + i] * h2[i];
+        resd[o] = 0.05f * tanhf(acc);                             // :39
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// sampling along the ray + world -> pose              inb_renderer.py:15-31, blend_utils.py:366-382
+// ---------------------------------------------------------------------------------------
+// torch.linspace(0, 1, S)[k] in fp32: step = 1/(S-1); first half start + k*step, second half
+// end - (S-1-k)*step (ATen's symmetric formula).
+NVR_HD float nvr_linspace01(int k, int S) {
+    if (S == 1) return 0.0f;
+    const float step = 1.0f / (float)(S - 1);
+    return (k < S / 2) ? (0.0f + step * (float)k) : (1.0f - step * (float)(S - 1 - k));
+}
+
+NVR_HD void nvr_ray_sample(const float o[3], const float d[3], float near_, float far_, int k, int S, float wp[3]) {
+    const float t = nvr_linspace01(k, S);
+    const float z = near_ * (1.0f - t) + far_ * t;               // :18
+#pragma unroll
+    for (int a = 0; a < 3; ++a) wp[a] = o[a] + d[a] * z;          // :29
+}
+
+// p = (w - Th) . R   (row vector times matrix), v = d . R
+NVR_HD void nvr_world_to_pose(const float* R, const float* Th, const float w[3], float p[3]) {
+    const float q[3] = {w[0] - Th[0], w[1] - Th[1], w[2] - Th[2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = (q[0] * R[0 * 3 + c] + q[1] * R[1 * 3 + c]) + q[2] * R[2 * 3 + c];
+}
+NVR_HD void nvr_dir_to_pose(const float* R, const float d[3], float v[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (d[0] * R[0 * 3 + c] + d[1] * R[1 * 3 + c]) + d[2] * R[2 * 3 + c];
+}

@@ -1,0 +1,248 @@
+"""Host-side engine: marshals PyTorch tensors into the C-ABI of ``libnvr_b200.so``.
+
+PyTorch is plumbing here (device memory, the current CUDA stream); all arithmetic of the path runs
+in the CUDA library.  Parameter and frame tensors are *borrowed*: the engine keeps Python
+references so the storages outlive the binding, and re-binds when a storage pointer changes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import cabi
+from .config import NUM_PARTS, PathConfig
+
+_FRAME_KEYS = ("R", "Th", "pbw", "pbounds", "part_pts", "part_pbw", "lengths2", "A", "big_A", "tuv", "tbounds",
+               "frame_dim", "latent_index")
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
+    if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+class Engine:
+    def __init__(self, cfg: PathConfig, device: Optional[torch.device] = None, max_points_per_pass: int = 8 << 20,
+                 mlp_mode: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("instant_nvr_b200 needs a CUDA device: the hot path has no CPU implementation")
+        cfg.check_supported()
+        self.cfg = cfg
+        self.lib = cabi.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.max_points_per_pass = int(max_points_per_pass)
+        conf = cabi.NvrConfig(cabi.ABI_VERSION, self.device.index or 0, float(cfg.smpl_thresh), int(mlp_mode))
+        h = C.c_void_p()
+        rc = self.lib.nvr_create(C.byref(conf), C.byref(h))
+        if rc != 0 or not h.value:
+            raise RuntimeError(f"nvr_create failed with code {rc}")
+        self._h = h
+        self._params_key = None
+        self._params_keep = None
+        self._frame_key = None
+        self._frame_keep = None
+        self._ws: Optional[torch.Tensor] = None
+        self._io: Optional[torch.Tensor] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.nvr_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self.lib.nvr_last_error(self._h)
+            raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+    # ---- parameters --------------------------------------------------------------------------
+    def invalidate_params(self) -> None:
+        self._params_key = None
+
+    def bind_params(self, net) -> None:
+        """``net``: instant_nvr_b200.network.Network (or any module with the same tree)."""
+        tensors = [p for p in net.parameters()]
+        key = tuple(p.data_ptr() for p in tensors)
+        if key == self._params_key:
+            return
+        for name, p in net.named_parameters():
+            if p.device != self.device:
+                raise RuntimeError(f"parameter {name} is on {p.device}, engine is on {self.device} "
+                                   "(move the module with .cuda(); there is no CPU path)")
+            if not p.is_contiguous():
+                raise RuntimeError(f"parameter {name} is not contiguous")
+        P = cabi.NvrParams()
+        for i, part in enumerate(net.tpose_human.part_networks):
+            d = P.part[i]
+            d.grid = cabi.grid_desc(part.embedder)
+            for k, lin in enumerate(part.occ.linears):
+                d.occ[k] = cabi.linear_desc(lin)
+            for k, lin in enumerate(part.rgb.linears):
+                d.rgb[k] = cabi.linear_desc(lin)
+            d.n_rgb = len(part.rgb.linears)
+            d.n_latent = part.rgb_latent.shape[0]
+            d.rgb_latent = part.rgb_latent.data_ptr()
+        P.deformer_grid = cabi.grid_desc(net.tpose_deformer.embedder)
+        for k, idx in enumerate((0, 2, 4)):
+            P.deformer_mlp[k] = cabi.linear_desc(net.tpose_deformer.mlp[idx])
+        self._check(self.lib.nvr_bind_params(self._h, C.byref(P)), "nvr_bind_params")
+        self._params_key, self._params_keep = key, tensors
+
+    # ---- frame --------------------------------------------------------------------------------
+    def bind_frame(self, batch: Dict) -> None:
+        src = [batch[k] for k in _FRAME_KEYS]
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in src)
+        if key == self._frame_key:
+            return
+        dev = self.device
+        t = {k: batch[k] for k in _FRAME_KEYS}
+        for k in ("pbw", "part_pts", "part_pbw", "tuv", "A", "big_A", "R", "Th", "pbounds", "tbounds", "lengths2"):
+            if t[k].shape[0] != 1:
+                raise ValueError(f"batch['{k}'] must have a leading batch dim of 1 (reference asserts n_batch == 1)")
+        keep = {
+            "R": _dev_f32(t["R"][0], dev), "Th": _dev_f32(t["Th"][0].reshape(3), dev),
+            "pbw": _dev_f32(t["pbw"][0], dev), "pbounds": _dev_f32(t["pbounds"][0], dev),
+            "part_pts": _dev_f32(t["part_pts"][0], dev), "part_pbw": _dev_f32(t["part_pbw"][0], dev),
+            "lengths2": t["lengths2"][0].to(device=dev, dtype=torch.int64).contiguous(),
+            "A": _dev_f32(t["A"][0], dev), "big_A": _dev_f32(t["big_A"][0], dev),
+            "tuv": _dev_f32(t["tuv"][0], dev), "tbounds": _dev_f32(t["tbounds"][0], dev),
+            "frame_dim": _dev_f32(t["frame_dim"].reshape(-1)[:1], dev),
+            "latent_index": t["latent_index"].reshape(-1)[:1].to(device=dev, dtype=torch.int64).contiguous(),
+        }
+        if keep["part_pts"].shape[0] != NUM_PARTS or keep["part_pbw"].shape[-1] != 24 or keep["tuv"].shape[-1] != 2:
+            raise ValueError("part_pts must be (1,5,maxlen,3), part_pbw (1,5,maxlen,24), tuv (1,D,H,W,2)")
+        F = cabi.NvrFrame()
+        F.R, F.Th = keep["R"].data_ptr(), keep["Th"].data_ptr()
+        F.pbw, F.pbounds = keep["pbw"].data_ptr(), keep["pbounds"].data_ptr()
+        for a in range(3):
+            F.pbw_dims[a] = keep["pbw"].shape[a]
+            F.tuv_dims[a] = keep["tuv"].shape[a]
+        F.pbw_channels = keep["pbw"].shape[3]
+        F.part_pts, F.part_pbw = keep["part_pts"].data_ptr(), keep["part_pbw"].data_ptr()
+        F.lengths2, F.maxlen = keep["lengths2"].data_ptr(), keep["part_pts"].shape[1]
+        F.A, F.big_A = keep["A"].data_ptr(), keep["big_A"].data_ptr()
+        F.tuv, F.tbounds = keep["tuv"].data_ptr(), keep["tbounds"].data_ptr()
+        F.frame_dim, F.latent_index = keep["frame_dim"].data_ptr(), keep["latent_index"].data_ptr()
+        self._check(self.lib.nvr_bind_frame(self._h, C.byref(F), _stream_ptr()), "nvr_bind_frame")
+        self._frame_key, self._frame_keep = key, keep
+
+    # ---- scratch --------------------------------------------------------------------------------
+    def _workspace(self, n_points: int) -> Tuple[int, int]:
+        n = max(64, min(int(n_points), self.max_points_per_pass))
+        need = int(self.lib.nvr_workspace_bytes(self._h, n))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws.data_ptr(), self._ws.numel()
+
+    # ---- entry points ----------------------------------------------------------------------------
+    def query_points(self, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict):
+        """Network.forward (eval): (N,3),(N,3) -> raw (N,4), occ (N,1) on the device."""
+        self.bind_frame(batch)
+        wpts, viewdir = _dev_f32(wpts, self.device), _dev_f32(viewdir, self.device)
+        n = wpts.shape[0]
+        raw = torch.empty(n, 4, dtype=torch.float32, device=self.device)
+        occ = torch.empty(n, 1, dtype=torch.float32, device=self.device)
+        ws, ws_bytes = self._workspace(n)
+        self._check(self.lib.nvr_query_points(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, raw.data_ptr(),
+                                              occ.data_ptr(), ws, ws_bytes, _stream_ptr()), "nvr_query_points")
+        return raw, occ
+
+    def render_rays(self, ray_o, ray_d, near, far, n_samples: int, batch: Optional[Dict] = None, want_raw: bool = False):
+        """Renderer.render (eval): rays (R,3),(R,3),(R,),(R,) -> rgb_map (R,3), acc_map (R,) [, raw (R*S,4)]."""
+        if batch is not None:
+            self.bind_frame(batch)
+        ray_o, ray_d = _dev_f32(ray_o, self.device), _dev_f32(ray_d, self.device)
+        near, far = _dev_f32(near, self.device), _dev_f32(far, self.device)
+        R = ray_o.shape[0]
+        rgb = torch.empty(R, 3, dtype=torch.float32, device=self.device)
+        acc = torch.empty(R, dtype=torch.float32, device=self.device)
+        raw = torch.empty(R * n_samples, 4, dtype=torch.float32, device=self.device) if want_raw else None
+        ws, ws_bytes = self._workspace(R * n_samples)
+        self._check(self.lib.nvr_render_rays(self._h, ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(), far.data_ptr(),
+                                             R, int(n_samples), rgb.data_ptr(), acc.data_ptr(),
+                                             raw.data_ptr() if want_raw else None, ws, ws_bytes, _stream_ptr()),
+                    "nvr_render_rays")
+        return (rgb, acc, raw) if want_raw else (rgb, acc)
+
+    def render_rays_host(self, ray_o, ray_d, near, far, n_samples: int, rgb_out, acc_out) -> None:
+        """Host (pinned) ray buffers in, host rgb_map / acc_map out; copies are part of the call."""
+        for t in (ray_o, ray_d, near, far, rgb_out, acc_out):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("render_rays_host takes contiguous fp32 CPU tensors")
+        R = ray_o.shape[0]
+        if self._io is None or self._io.numel() < 12 * R:
+            self._io = torch.empty(12 * R, dtype=torch.float32, device=self.device)
+        ws, ws_bytes = self._workspace(R * n_samples)
+        self._check(self.lib.nvr_render_rays_host(self._h, ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(),
+                                                  far.data_ptr(), R, int(n_samples), rgb_out.data_ptr(), acc_out.data_ptr(),
+                                                  self._io.data_ptr(), ws, ws_bytes, _stream_ptr()), "nvr_render_rays_host")
+
+    def deformer_residual(self, tpts: torch.Tensor, batch: Dict) -> torch.Tensor:
+        self.bind_frame(batch)
+        tpts = _dev_f32(tpts, self.device)
+        out = torch.empty_like(tpts)
+        self._check(self.lib.nvr_deformer_residual(self._h, tpts.data_ptr(), tpts.shape[0], out.data_ptr(), _stream_ptr()),
+                    "nvr_deformer_residual")
+        return out
+
+    def embed_part(self, part: int, xyz: torch.Tensor) -> torch.Tensor:
+        xyz = _dev_f32(xyz, self.device)
+        out = torch.empty(xyz.shape[0], 19, dtype=torch.float32, device=self.device)
+        self._check(self.lib.nvr_embed_part(self._h, int(part), xyz.data_ptr(), xyz.shape[0], out.data_ptr(), _stream_ptr()),
+                    "nvr_embed_part")
+        return out
+
+    def part_mlp(self, part: int, emb: torch.Tensor, dirs: torch.Tensor, batch: Dict) -> torch.Tensor:
+        """occ + rgb MLPs of one part on explicit (n,19) embeddings and (n,3) canonical view dirs -> raw (n,4)."""
+        self.bind_frame(batch)
+        n = emb.shape[0]
+        e20 = torch.zeros(n, 20, dtype=torch.float32, device=self.device)
+        e20[:, :19] = _dev_f32(emb, self.device)
+        dirs = _dev_f32(dirs, self.device)
+        raw = torch.empty(n, 4, dtype=torch.float32, device=self.device)
+        ws, ws_bytes = self._workspace(n)
+        self._check(self.lib.nvr_part_mlp(self._h, int(part), e20.data_ptr(), dirs.data_ptr(), n, raw.data_ptr(), ws, ws_bytes,
+                                          _stream_ptr()), "nvr_part_mlp")
+        return raw
+
+    def query_points_debug(self, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict):
+        """query_points + per-stage taps: raw (N,4), surv_of_sample (N,), warp (N,5,8)=[flag,x,y,z,vx,vy,vz,pdist]."""
+        self.bind_frame(batch)
+        wpts, viewdir = _dev_f32(wpts, self.device), _dev_f32(viewdir, self.device)
+        n = wpts.shape[0]
+        raw = torch.empty(n, 4, dtype=torch.float32, device=self.device)
+        surv = torch.empty(n, dtype=torch.int32, device=self.device)
+        warp = torch.empty(n, 5, 8, dtype=torch.float32, device=self.device)
+        keep, self.max_points_per_pass = self.max_points_per_pass, max(self.max_points_per_pass, n)
+        ws, ws_bytes = self._workspace(n)
+        self.max_points_per_pass = keep
+        self._check(self.lib.nvr_query_points_debug(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, raw.data_ptr(),
+                                                    surv.data_ptr(), warp.data_ptr(), ws, ws_bytes, _stream_ptr()),
+                    "nvr_query_points_debug")
+        return raw, surv, warp
+
+    def profile(self, enable: bool) -> None:
+        self._check(self.lib.nvr_profile(self._h, int(enable)), "nvr_profile")
+
+    def profile_read(self) -> Dict:
+        p = cabi.NvrStageProfile()
+        self._check(self.lib.nvr_profile_read(self._h, C.byref(p)), "nvr_profile_read")
+        return {"ms": dict(zip(cabi.STAGE_NAMES, list(p.ms))), "launches": dict(zip(cabi.STAGE_NAMES, list(p.launches))),
+                "passes": p.passes, "survivors": p.survivors, "pairs": list(p.pairs)}
+
+    def counters(self) -> Dict[str, int]:
+        c = cabi.NvrCounters()
+        self._check(self.lib.nvr_read_counters(self._h, C.byref(c), _stream_ptr()), "nvr_read_counters")
+        return {"n_points": c.n_points, "n_survivors": c.n_survivors, "n_pairs": list(c.n_pairs),
+                "kernel_launches": c.kernel_launches}

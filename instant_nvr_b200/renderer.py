@@ -1,0 +1,47 @@
+"""Drop-in for ``lib.networks.renderer.inb_renderer.Renderer`` (reference
+``inb_renderer.py:11-239``), selected with ``renderer_module: instant_nvr_b200.renderer``
+(``lib/networks/renderer/make_renderer.py:5-16``).
+
+``render(batch)`` runs sampling, the network and the compositing in the CUDA library in one
+call over *all* rays (the reference's 4096-ray Python loop only existed to bound its 8 KiB/point
+intermediate, ``inb_renderer.py:217-237``; the library splits passes itself by workspace size).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .network import Network
+
+
+class Renderer:
+    def __init__(self, net: Network, return_raw: bool = False, output_device: str = "cpu"):
+        self.net = net
+        self.return_raw = return_raw          # 'raw'/'occ' per sample (16 B/sample) only on request
+        self.output_device = output_device    # the reference hands every eval output back on the CPU (:199-200)
+
+    def render(self, batch: Dict, test: bool = False, epoch: int = -1) -> Dict[str, torch.Tensor]:
+        """batch: reference layout, leading batch dim 1 -- ray_o, ray_d (1,R,3), near, far (1,R) plus the
+        frame tensors.  Returns rgb_map (1,R,3), acc_map (1,R) and, with
+        ``return_raw``, raw (1,R*S,4), occ (1,R*S,1)."""
+        net = self.net
+        if net.training:
+            raise NotImplementedError(
+                "training-mode render (stratified jitter, pair / distortion regularisers, autograd) is "
+                "SURVEY.md section 8(f) item 1; this build provides the eval path only")
+        if epoch != -1:
+            batch["epoch"] = epoch
+        ray_o, ray_d, near, far = batch["ray_o"], batch["ray_d"], batch["near"], batch["far"]
+        if ray_o.shape[0] != 1:
+            raise ValueError("n_batch must be 1 (the reference asserts it, inb_part_network_multiassign.py:84)")
+        net._maybe_update_bounds(batch)
+        S = net.cfg.N_samples
+        out = net.engine().render_rays(ray_o[0], ray_d[0], near[0], far[0], S, batch=batch, want_raw=self.return_raw)
+        ret = {"rgb_map": out[0][None], "acc_map": out[1][None]}
+        if self.return_raw:
+            ret["raw"] = out[2][None]
+            ret["occ"] = out[2][None, :, 3:4].contiguous()
+        if self.output_device is not None:
+            ret = {k: v.detach().to(self.output_device) for k, v in ret.items()}
+        return ret

@@ -213,24 +213,28 @@ def make_frame(seed: int = 0, n_verts: int = 6890, pose_scale: float = 0.2, voxe
 
 
 def make_rays(frame: Dict[str, torch.Tensor], H: int, W: int, cam_dist: float = 3.0,
-              tile: Tuple[int, int, int, int] | None = None) -> Dict[str, torch.Tensor]:
+              tile: Tuple[int, int, int, int] | None = None, azimuth_deg: float = 0.0) -> Dict[str, torch.Tensor]:
     """Pinhole rays, one per pixel of an H x W image whose frustum just covers the world bbox.
     ``tile=(r0, r1, c0, c1)`` keeps only that pixel window (bounded CPU-baseline samples).
+    ``azimuth_deg`` orbits the camera around the vertical axis (multi-view batches).
     Returns ray_o, ray_d (1,R,3), near, far, occupancy (1,R); rays that miss the bbox get a
     degenerate near == far interval at the bbox centre depth (the reference would drop them
     via mask_at_box; keeping them fixes R = H*W for the benchmark)."""
     wb = frame["wbounds"][0].double().numpy()
     centre = wb.mean(0)
     half = (wb[1] - wb[0]) / 2
-    eye = centre + np.array([0.0, 0.0, cam_dist])
-    # image plane at the bbox centre depth spans the bbox's x/y extent with a 5 % margin
-    span = 1.05 * max(half[0], half[1])
+    az = np.deg2rad(azimuth_deg)
+    fwd = np.array([np.sin(az), 0.0, np.cos(az)])           # from the bbox centre towards the camera
+    right = np.array([np.cos(az), 0.0, -np.sin(az)])
+    eye = centre + cam_dist * fwd
+    # image plane through the bbox centre spans the bbox's horizontal / vertical extent with a 5 % margin
+    span = 1.05 * max(abs(half[0] * right[0]) + abs(half[2] * right[2]), half[1])
     ys = (np.arange(H) + 0.5) / H * 2 - 1
     xs = (np.arange(W) + 0.5) / W * 2 - 1
     if tile is not None:
         ys, xs = ys[tile[0]:tile[1]], xs[tile[2]:tile[3]]
     px, py = np.meshgrid(xs * span, -ys * span)       # row 0 is the top of the image
-    target = np.stack([centre[0] + px, centre[1] + py, np.full_like(px, centre[2])], -1).reshape(-1, 3)
+    target = (centre[None, None] + px[..., None] * right + py[..., None] * np.array([0.0, 1.0, 0.0])).reshape(-1, 3)
     d = target - eye
     d /= np.linalg.norm(d, axis=1, keepdims=True)     # normalised as in if_nerf_data_utils.py:36
     o = np.broadcast_to(eye, d.shape)

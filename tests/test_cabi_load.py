@@ -1,0 +1,67 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads without a GPU, exports every
+symbol include/nvr_b200.h declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import REPO
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from instant_nvr_b200 import cabi
+    return cabi.load()
+
+
+def declared_functions():
+    text = open(os.path.join(REPO, "include", "nvr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nvr_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from instant_nvr_b200 import cabi
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/nvr_b200.h but not exported"
+        assert n in cabi.SYMBOLS, f"{n} has no ctypes prototype"
+    assert sorted(cabi.SYMBOLS) == names
+
+
+def test_abi_version(lib):
+    assert lib.nvr_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(lib):
+    from instant_nvr_b200 import cabi
+    from instant_nvr_b200.config import PathConfig
+    from instant_nvr_b200.engine import Engine
+    conf = cabi.NvrConfig(cabi.ABI_VERSION, 0, 0.05, 0)
+    h = C.c_void_p()
+    assert lib.nvr_create(C.byref(conf), C.byref(h)) != 0 and not h.value
+    with pytest.raises(RuntimeError):
+        Engine(PathConfig.inb_377(log2_T_cap=10))
+
+
+def test_bad_abi_version_rejected(lib):
+    from instant_nvr_b200 import cabi
+    conf = cabi.NvrConfig(99, 0, 0.05, 0)
+    h = C.c_void_p()
+    assert lib.nvr_create(C.byref(conf), C.byref(h)) == 3
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under instant_nvr_b200/ may reference it."""
+    pkg = os.path.join(REPO, "instant_nvr_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "nvr_oracle" not in text and "import oracle" not in text, os.path.join(root, f)

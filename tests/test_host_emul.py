@@ -1,0 +1,228 @@
+"""Per-sample device arithmetic (csrc/nvr_math.cuh) compiled for the host and checked against
+the oracle -- runs without a GPU.
+
+tests/host_emul/emul.cpp is a TEST-ONLY harness: it compiles the same ``__host__ __device__``
+statements the CUDA kernels execute per sample with g++ (-ffp-contract=off) so index arithmetic,
+trilinear / KNN / LBS / deformer math can be debugged in the CPU container.  It is not shipped,
+not loaded by the product and not a fallback.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO
+
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+import nvr_oracle as O  # noqa: E402
+from instant_nvr_b200 import cabi  # noqa: E402
+
+EMUL_DIR = os.path.join(REPO, "tests", "host_emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(EMUL_DIR, "libnvr_emul.so")
+    src = os.path.join(EMUL_DIR, "emul.cpp")
+    deps = [src, os.path.join(REPO, "instant_nvr_b200", "csrc", "nvr_math.cuh"), os.path.join(REPO, "include", "nvr_b200.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    return C.CDLL(so)
+
+
+def fp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def test_struct_sizes_match_header(emul):
+    for which, cls in enumerate((cabi.NvrGrid, cabi.NvrLinear, cabi.NvrPart, cabi.NvrParams, cabi.NvrFrame,
+                                 cabi.NvrConfig, cabi.NvrCounters, cabi.NvrStageProfile)):
+        assert emul.emul_sizeof(which) == C.sizeof(cls), cls.__name__
+
+
+def test_barrett_mod(emul):
+    rng = np.random.default_rng(0)
+    for T in (16411, 32771, 65537, 262147, 1048583):
+        ix, iy, iz = (rng.integers(0, 2100, 200000) for _ in range(3))
+        h = (ix * 1) ^ (iy * 19349663) ^ (iz * 83492791)
+        h = np.concatenate([h, [0, T - 1, T, T + 1, 2 * T - 1, 2**40, 2**62 + 12345]]).astype(np.int64)
+        emul.emul_check_mod.restype = C.c_longlong
+        bad = emul.emul_check_mod(C.c_longlong(T), h.ctypes.data_as(C.c_void_p), C.c_longlong(len(h)))
+        assert bad == 0, T
+
+
+def _embed(emul, gp, x):
+    g = cabi.grid_desc(gp)
+    out = torch.empty(x.shape[0], gp.out_dim)
+    emul.emul_embed(C.byref(g), fp(x), C.c_longlong(x.shape[0]), fp(out), C.c_int(gp.out_dim))
+    return out
+
+
+def _embed_f64(sd, prefix, x, sum_features):
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items() if k.startswith(prefix)}
+    return O.grid_embed(sd64, prefix, x.double(), sum_features)
+
+
+def test_grid_embed_matches_oracle(emul, golden_setup):
+    """Inside the bbox the emulated device arithmetic and the oracle agree to ~1 ulp of the result.
+    Outside it the reference extrapolates with corner weights of magnitude (1+|o|)^3 and opposite
+    signs, so its own fp32 result is summation-order noise; there we only require that our error
+    against exact (fp64) arithmetic is of the same size as the oracle's."""
+    net, sd = golden_setup["net"], golden_setup["sd"]
+    g = torch.Generator().manual_seed(3)
+    for pid in range(5):
+        gp = net.tpose_human.part_networks[pid].embedder
+        pre = f"tpose_human.part_networks.{pid}.embedder."
+        lo, hi = gp.bounds[0], gp.bounds[1]
+        x = (lo + (hi - lo) * (torch.rand(700, 3, generator=g) * 1.4 - 0.2)).contiguous()
+        x[:8] = torch.stack([lo, hi, lo - 1, hi + 1, (lo + hi) / 2, lo + 1e-7, hi - 1e-7, hi * 0 + 5.0])   # edges / far out
+        ours = _embed(emul, gp, x)
+        ref = O.grid_embed(sd, pre, x, True)
+        u = (x - lo) / (hi - lo)
+        inside = ((u >= 0) & (u <= 1)).all(1)
+        assert inside.sum() > 100
+        assert torch.allclose(ours[inside], ref[inside], atol=2e-6, rtol=1e-5), (pid, (ours - ref)[inside].abs().max())
+        assert torch.equal(ours[:, :3], ref[:, :3])
+        exact = _embed_f64(sd, pre, x, True)
+        e_ours = (ours.double() - exact)[~inside].pow(2).mean().sqrt()
+        e_ref = (ref.double() - exact)[~inside].pow(2).mean().sqrt()
+        assert e_ours <= 3 * e_ref + 1e-6, (pid, float(e_ours), float(e_ref))
+    gp = net.tpose_deformer.embedder
+    x = (torch.rand(500, 3, generator=g) * 1.3 - 0.15).contiguous()
+    ours = _embed(emul, gp, x)
+    ref = O.grid_embed(sd, "tpose_deformer.embedder.", x, False)
+    inside = ((x >= 0) & (x <= 1)).all(1)
+    assert torch.allclose(ours[inside], ref[inside], atol=1e-6, rtol=1e-5), (ours - ref)[inside].abs().max()
+    exact = _embed_f64(sd, "tpose_deformer.embedder.", x, False)
+    e_ours = (ours.double() - exact)[~inside].pow(2).mean().sqrt()
+    e_ref = (ref.double() - exact)[~inside].pow(2).mean().sqrt()
+    assert e_ours <= 3 * e_ref + 1e-6
+
+
+def test_full_size_hash_indices(emul):
+    """The shipped body grid (T = 1048583, res up to 2005): int64 hash without wrap-around.  A small
+    table cannot be built at that T, so the table is an index-revealing ramp: every row holds
+    row_index / 16 in all 16 features, hence the level sum at a corner with weight 1 is the row."""
+    from instant_nvr_b200.config import PathConfig
+    spec = PathConfig.inb_377().parts[0].grid
+    T, sh = spec.T, spec.start_hash
+    res = spec.res
+    # emulate one hashed level with a private table: rows = T, value = row id (exact in fp32 < 2^24)
+    l = 15
+    table = (torch.arange(T, dtype=torch.float32) / 16.0)[:, None].expand(T, 16).contiguous()
+    g = cabi.NvrGrid()
+    bounds = torch.tensor([[0., 0., 0.], [1., 1., 1.]])
+    dense = torch.zeros(res[0] ** 3, 16)
+    g.dense, g.hash, g.bounds = dense.data_ptr(), table.data_ptr(), bounds.data_ptr()
+    g.n_levels, g.n_feat, g.start_hash, g.sum_features, g.table_size = 2, 16, 1, 1, T
+    g.res[0], g.size[0], g.dense_off[0] = res[0], float(np.float32(1 / (res[0] - 1))), 0
+    g.res[1], g.size[1], g.dense_off[1] = res[l], float(np.float32(1 / (res[l] - 1))), 0
+    rng = np.random.default_rng(1)
+    ijk = rng.integers(0, res[l] - 1, (4000, 3))
+    size = np.float32(1 / (res[l] - 1))
+    x = torch.from_numpy((ijk.astype(np.float32) + np.float32(0.25)) * size).contiguous()   # interior of the cell
+    out = torch.empty(x.shape[0], 5)
+    emul.emul_embed(C.byref(g), fp(x), C.c_longlong(x.shape[0]), fp(out), C.c_int(5))
+    # oracle with the same synthetic state dict
+    sd = {"g.bounds": bounds, "g.entries_size": torch.tensor([g.size[0], g.size[1]]),
+          "g.entries_num": torch.tensor([res[0], res[l]]), "g.entries_sum": torch.tensor([res[0] ** 3, 0]),
+          "g.dense": dense, "g.hash": table[None], "g.offsets": torch.tensor(
+              [[float((c >> 2) & 1), float((c >> 1) & 1), float(c & 1)] for c in range(8)])}
+    ref = O.grid_embed(sd, "g.", x, True)
+    assert torch.allclose(out, ref, rtol=2e-6, atol=1e-2), (out - ref).abs().max()
+    # and the defining property: a uint32-wrapping hash would land elsewhere for most of these
+    i = torch.from_numpy(ijk)
+    h64 = (i[:, 0] * 1 ^ i[:, 1] * 19349663 ^ i[:, 2] * 83492791) % T
+    h32 = ((i[:, 0] * 1 ^ i[:, 1] * 19349663 ^ i[:, 2] * 83492791) & 0xFFFFFFFF) % T
+    assert (h64 != h32).float().mean() > 0.5
+
+
+def test_volume_sampling(emul, golden_setup):
+    frame = golden_setup["frame"]
+    g = torch.Generator().manual_seed(4)
+    pb = frame["pbounds"][0]
+    pts = (pb[0] + (pb[1] - pb[0]) * (torch.rand(2000, 3, generator=g) * 1.4 - 0.2)).contiguous()
+    pts[:2] = torch.stack([pb[0], pb[1]])
+    vol = frame["pbw"][0].contiguous()
+    D, H, W, Cc = vol.shape
+    out = torch.empty(2000, 1)
+    emul.emul_sample_volume(fp(vol), D, H, W, Cc, fp(pb.contiguous()), Cc - 1, 1, fp(pts), C.c_longlong(2000), fp(out))
+    ref = O.sample_volume(vol[..., -1:], pts, pb)
+    assert torch.allclose(out, ref, atol=1e-6, rtol=1e-5), (out - ref).abs().max()
+    tb = frame["tbounds"][0]
+    tuv = frame["tuv"][0].contiguous()
+    pts = (tb[0] + (tb[1] - tb[0]) * (torch.rand(1000, 3, generator=g) * 1.2 - 0.1)).contiguous()
+    out = torch.empty(1000, 2)
+    emul.emul_sample_volume(fp(tuv), *tuv.shape, fp(tb.contiguous()), 0, 2, fp(pts), C.c_longlong(1000), fp(out))
+    assert torch.allclose(out, O.sample_volume(tuv, pts, tb), atol=1e-6, rtol=1e-5)
+
+
+def test_ray_points(emul, golden_setup):
+    frame, rays = golden_setup["frame"], golden_setup["rays"]
+    S = 32
+    o, d, n, f = (rays[k][0].contiguous() for k in ("ray_o", "ray_d", "near", "far"))
+    R = o.shape[0]
+    w, p = torch.empty(R * S, 3), torch.empty(R * S, 3)
+    Rm, Th = frame["R"][0].contiguous(), frame["Th"][0].reshape(3).contiguous()
+    emul.emul_ray_points(fp(o), fp(d), fp(n), fp(f), C.c_longlong(R), S, fp(Rm), fp(Th), fp(w), fp(p))
+    pts, _ = O.sample_along_rays(o, d, n, f, S)
+    assert torch.equal(w, pts.reshape(-1, 3))                      # bit-exact: same fp32 statements
+    ref_p = torch.matmul(pts.reshape(-1, 3) - frame["Th"][0], Rm)
+    assert torch.allclose(p, ref_p, atol=5e-7, rtol=1e-6)
+
+
+def test_knn_lbs(emul, golden_setup):
+    frame = golden_setup["frame"]
+    g = torch.Generator().manual_seed(5)
+    n = 300
+    q = frame["ppts"][0][torch.randperm(6890, generator=g)[:n - 50]] + 0.04 * torch.randn(n - 50, 3, generator=g)
+    pb = frame["pbounds"][0]
+    q = torch.cat([q, pb[0] + (pb[1] - pb[0]) * torch.rand(50, 3, generator=g)]).contiguous()
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).contiguous()
+    pp, pw = frame["part_pts"][0].contiguous(), frame["part_pbw"][0].contiguous()
+    ln = frame["lengths2"][0].contiguous()
+    A, bA = frame["A"][0].contiguous(), frame["big_A"][0].contiguous()
+    bw, pd = torch.empty(n, 5, 24), torch.empty(n, 5)
+    x0, v = torch.empty(n, 5, 3), torch.empty(n, 5, 3)
+    emul.emul_knn_lbs(fp(pp), fp(pw), fp(ln), pp.shape[1], fp(A), fp(bA), fp(q), fp(dirs), C.c_longlong(n),
+                      fp(bw), fp(pd), fp(x0), fp(v))
+    rbw, rpd = O.knn_blend_weights(q, pp, pw, ln)
+    assert torch.allclose(bw, rbw, atol=1e-6, rtol=1e-5), (bw - rbw).abs().max()
+    assert torch.allclose(pd, rpd, atol=1e-6, rtol=1e-5)
+    qe = q[:, None].expand(n, 5, 3).reshape(-1, 3)
+    de = dirs[:, None].expand(n, 5, 3).reshape(-1, 3)
+    rx0, rv = O.lbs_to_bigpose(qe, de, rbw.reshape(-1, 24), A, bA)
+    assert torch.allclose(x0.reshape(-1, 3), rx0, atol=1e-5, rtol=1e-4), (x0.reshape(-1, 3) - rx0).abs().max()
+    assert torch.allclose(v.reshape(-1, 3), rv, atol=1e-5, rtol=1e-4)
+
+
+def test_deformer(emul, golden_setup):
+    net, sd, frame = golden_setup["net"], golden_setup["sd"], golden_setup["frame"]
+    g = torch.Generator().manual_seed(6)
+    tb = frame["tbounds"][0]
+    x0 = (tb[0] + (tb[1] - tb[0]) * (torch.rand(400, 3, generator=g) * 1.2 - 0.1)).contiguous()
+    gd = cabi.grid_desc(net.tpose_deformer.embedder)
+    mlp = (cabi.NvrLinear * 3)(*[cabi.linear_desc(net.tpose_deformer.mlp[i]) for i in (0, 2, 4)])
+    tuv = frame["tuv"][0].contiguous()
+    out = torch.empty(400, 3)
+    emul.emul_deformer(C.byref(gd), mlp, fp(tuv), *tuv.shape[:3], fp(tb.contiguous()), C.c_float(float(frame["frame_dim"][0])),
+                       fp(x0), C.c_longlong(400), fp(out))
+    ref = O.deformer(sd, x0, tuv, tb, frame["frame_dim"])
+    assert torch.allclose(out, ref, atol=1e-6, rtol=1e-4), (out - ref).abs().max()
+
+
+def test_posenc_and_activations(emul):
+    g = torch.Generator().manual_seed(7)
+    v = torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=-1).contiguous()
+    out = torch.empty(256, 27)
+    emul.emul_posenc(fp(v), C.c_longlong(256), fp(out))
+    assert torch.allclose(out, O.posenc(v), atol=1e-6)
+    x = torch.cat([torch.linspace(-30, 30, 999), torch.tensor([19.999, 20.0, 20.001])]).contiguous()
+    sp, sg = torch.empty_like(x), torch.empty_like(x)
+    emul.emul_activations(fp(x), C.c_longlong(x.numel()), fp(sp), fp(sg))
+    assert torch.allclose(sp, torch.nn.functional.softplus(x), rtol=2e-6, atol=1e-30)
+    assert torch.allclose(sg, torch.sigmoid(x), rtol=2e-6, atol=1e-30)
