@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 1
+#define NVR_ABI_VERSION 2
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -178,11 +178,12 @@ int nvr_query_points_debug(NvrHandle h, const float* wpts, const float* viewdir,
  * record a CUDA-event pair on its stream; nvr_profile_read synchronises the device and sums them. */
 #define NVR_STAGE_PREP 0
 #define NVR_STAGE_CULL 1
-#define NVR_STAGE_WARP 2
-#define NVR_STAGE_EMBED 3     /* the grid gather */
-#define NVR_STAGE_MLP 4
-#define NVR_STAGE_RESOLVE 5
-#define NVR_NUM_STAGES 6
+#define NVR_STAGE_KNN 2       /* 4-NN search + blend-weight flags */
+#define NVR_STAGE_WARP 3      /* LBS + deformer */
+#define NVR_STAGE_EMBED 4     /* the grid gather */
+#define NVR_STAGE_MLP 5
+#define NVR_STAGE_RESOLVE 6
+#define NVR_NUM_STAGES 7
 typedef struct NvrStageProfile {
     double ms[NVR_NUM_STAGES];            /* summed launch durations */
     int64_t launches[NVR_NUM_STAGES];

@@ -12,7 +12,7 @@ from typing import Optional
 
 MAX_LEVELS = 16
 NUM_PARTS = 5
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnvr_b200.so")
@@ -67,11 +67,11 @@ class NvrCounters(C.Structure):
 
 
 class NvrStageProfile(C.Structure):
-    _fields_ = [("ms", C.c_double * 6), ("launches", C.c_int64 * 6), ("passes", C.c_int64), ("survivors", C.c_int64),
+    _fields_ = [("ms", C.c_double * 7), ("launches", C.c_int64 * 7), ("passes", C.c_int64), ("survivors", C.c_int64),
                 ("pairs", C.c_int64 * NUM_PARTS)]
 
 
-STAGE_NAMES = ("prep", "cull", "warp", "embed", "mlp", "resolve")
+STAGE_NAMES = ("prep", "cull", "knn", "warp", "embed", "mlp", "resolve")
 
 # name -> (restype, argtypes); exactly the declarations of include/nvr_b200.h
 SYMBOLS = {

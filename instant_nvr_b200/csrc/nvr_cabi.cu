@@ -27,8 +27,8 @@ struct NvrEngine {
     FrameDev fdev;
     // per-frame device buffers owned by the engine (grow-only)
     float* d_dist = nullptr; size_t dist_cap = 0;
-    float4* d_verts = nullptr; size_t verts_cap = 0;
-    int* d_part_off = nullptr;
+    float4* d_verts = nullptr; size_t verts_cap = 0;      // clustered vertices + 2 AABB corners per cluster
+    int* d_cl_off = nullptr;
     int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
     long long launches = 0;
     long long last_points = 0;
@@ -81,7 +81,14 @@ static GridDev to_dev(const NvrGrid& g) {
     d.n_levels = g.n_levels; d.n_feat = g.n_feat; d.start_hash = g.start_hash; d.sum_features = g.sum_features;
     d.T = (unsigned long long)g.table_size;
     d.T_magic = g.table_size > 1 ? (unsigned long long)((((unsigned __int128)1) << 64) / (unsigned __int128)g.table_size) : 0ull;
-    for (int l = 0; l < NVR_MAX_LEVELS; ++l) { d.res[l] = g.res[l]; d.size[l] = g.size[l]; d.dense_off[l] = g.dense_off[l]; }
+    int max_res = 0;
+    for (int l = 0; l < NVR_MAX_LEVELS; ++l) {
+        d.res[l] = g.res[l]; d.size[l] = g.size[l]; d.dense_off[l] = g.dense_off[l];
+        if (l < g.n_levels) max_res = std::max(max_res, g.res[l]);
+    }
+    // 32-bit modulo (nvr_mod_T40) needs hash values < 2^40 (coordinates < 2^13) and 2^8 < T < 2^31
+    d.T_magic40 = (max_res <= 8192 && g.table_size > 256 && g.table_size < (1ll << 31))
+                      ? (unsigned int)((1ull << 40) / (unsigned long long)g.table_size) : 0u;
     return d;
 }
 static LinearDev to_dev(const NvrLinear& l) { return LinearDev{l.weight, l.bias, l.in_dim, l.out_dim}; }
@@ -101,10 +108,11 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
     h->cfg = *cfg;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
-    if (cudaSetDevice(cfg->device) != cudaSuccess || cudaMalloc(&h->d_part_off, 8 * sizeof(int)) != cudaSuccess ||
+    if (cudaSetDevice(cfg->device) != cudaSuccess || cudaMalloc(&h->d_cl_off, 8 * sizeof(int)) != cudaSuccess ||
         cudaMalloc(&h->d_counters_snapshot, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
         cudaMemset(h->d_counters_snapshot, 0, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES) != cudaSuccess) {
+        cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_SORT_MAX * 8) != cudaSuccess) {
         cudaGetLastError();
         delete h;
         return 5;
@@ -116,7 +124,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
 extern "C" int nvr_destroy(NvrHandle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_part_off); cudaFree(h->d_counters_snapshot);
+    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_counters_snapshot);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
     delete h;
@@ -139,6 +147,11 @@ extern "C" int nvr_bind_params(NvrHandle h, const NvrParams* p) {
             pt.rgb[pt.n_rgb - 1].out_dim != 3 || (pt.n_rgb == 3 && (pt.rgb[1].in_dim != 64 || pt.rgb[1].out_dim != 64)))
             return fail(h, "nvr_bind_params: rgb MLP must be 70->64[->64]->3");
         if (!g.dense || !g.hash || !g.bounds || !pt.rgb_latent) return fail(h, "nvr_bind_params: null table pointer");
+        if (g.table_size < 2 || (long long)(g.n_levels - g.start_hash) * g.table_size >= (1ll << 32))
+            return fail(h, "nvr_bind_params: hashed levels must have fewer than 2^32 rows in total");
+        for (int l = 0; l < g.start_hash && l < g.n_levels; ++l)
+            if (g.dense_off[l] < 0 || g.dense_off[l] + (long long)g.res[l] * g.res[l] * g.res[l] >= (1ll << 31))
+                return fail(h, "nvr_bind_params: dense levels must have fewer than 2^31 rows in total");
     }
     const NvrGrid& dg = p->deformer_grid;
     if (dg.n_feat != 2 || dg.sum_features || dg.n_levels != 8 || dg.start_hash < 1)
@@ -169,11 +182,13 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
         !f->big_A || !f->tuv || !f->tbounds || !f->frame_dim || !f->latent_index)
         return fail(h, "nvr_bind_frame: null tensor pointer");
     if (f->pbw_channels < 1 || f->maxlen < 1) return fail(h, "nvr_bind_frame: bad pbw_channels / maxlen");
+    if (f->maxlen > NVR_SORT_MAX) return fail(h, "nvr_bind_frame: a part with more than 8192 vertices is not supported");
     for (int a = 0; a < 3; ++a)
         if (f->pbw_dims[a] < 1 || f->tuv_dims[a] < 1) return fail(h, "nvr_bind_frame: bad volume dims");
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
     const size_t n_vox = (size_t)f->pbw_dims[0] * f->pbw_dims[1] * f->pbw_dims[2];
-    const size_t n_verts = (size_t)NVR_NUM_PARTS * f->maxlen;
+    const size_t max_cl = (size_t)NVR_NUM_PARTS * ((f->maxlen + NVR_CL - 1) / NVR_CL);
+    const size_t n_verts = max_cl * NVR_CL + 2 * max_cl;   // float4 slots: vertices, then cl_lo, then cl_hi
     if (n_vox > h->dist_cap) {
         NVR_CHECK(h, cudaFree(h->d_dist));
         h->d_dist = nullptr; h->dist_cap = 0;
@@ -187,17 +202,20 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
         h->verts_cap = n_verts;
     }
     StageTimer tm_(h, stream, NVR_STAGE_PREP);
-    k_frame_prep<<<std::min<int>(h->sm_count * 4, (int)((std::max(n_vox, n_verts) + 255) / 256)), 256, 0, stream>>>(
-        f->pbw, (int)n_vox, f->pbw_channels, h->d_dist, f->part_pts, (const long long*)f->lengths2, f->maxlen,
-        h->d_verts, h->d_part_off);
+    k_frame_prep<<<std::min<int>(h->sm_count * 4, (int)((n_vox + 255) / 256)), 256, 0, stream>>>(
+        f->pbw, (int)n_vox, f->pbw_channels, h->d_dist);
+    float4* cl_lo = h->d_verts + max_cl * NVR_CL;
+    float4* cl_hi = cl_lo + max_cl;
+    k_cluster_verts<<<NVR_NUM_PARTS, 1024, NVR_SORT_MAX * 8, stream>>>(f->part_pts, (const long long*)f->lengths2, f->maxlen,
+                                                                      h->d_verts, cl_lo, cl_hi, h->d_cl_off);
     NVR_CHECK(h, cudaGetLastError());
-    h->launches++;
+    h->launches += 2;
     h->frame = *f;
     FrameDev& d = h->fdev;
     d.R = f->R; d.Th = f->Th;
     d.dist = VolumeDev{h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], 1, f->pbounds};
     d.tuv = VolumeDev{f->tuv, f->tuv_dims[0], f->tuv_dims[1], f->tuv_dims[2], 2, f->tbounds};
-    d.verts = h->d_verts; d.part_off = h->d_part_off; d.part_pbw = f->part_pbw; d.maxlen = f->maxlen;
+    d.verts = h->d_verts; d.cl_lo = cl_lo; d.cl_hi = cl_hi; d.cl_off = h->d_cl_off; d.part_pbw = f->part_pbw; d.maxlen = f->maxlen;
     d.A = f->A; d.bigA = f->big_A; d.frame_dim = f->frame_dim; d.latent_index = (const long long*)f->latent_index;
     h->have_frame = true;
     return 0;
@@ -248,21 +266,25 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     { StageTimer t(h, st, NVR_STAGE_CULL);
     k_cull<<<grid_for(n, 256, sm * 16), 256, 0, st>>>(h->fdev, pts, ray_d, near_, far_, n, n_samples, h->cfg.smpl_thresh,
                                                       w.counters, w.surv_of_sample, w.surv); }
+    // neighbour records alias the embedding buffer: they are consumed by k_warp before k_embed writes it
+    KnnRec* recs = (KnnRec*)w.emb;
+    { StageTimer t(h, st, NVR_STAGE_KNN);
+    k_knn<<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg); }
     { StageTimer t(h, st, NVR_STAGE_WARP);
-    k_warp<<<grid_for(n, 128, sm * 8), 128, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, h->cfg.smpl_thresh,
-                                                     w.counters, w.surv, w.pairs, (int)w.cap, w.raws, dbg); }
+    k_warp<<<dim3(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS), WARP_THREADS, 0, st>>>(
+        h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg); }
     for (int p = 0; p < NVR_NUM_PARTS; ++p) {
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
         { StageTimer t(h, st, NVR_STAGE_EMBED);
-        k_embed<<<grid_for(n, 64, sm * 8), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
+        k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
                                                          el, NVR_EMB_STRIDE); }
         StageTimer t(h, st, NVR_STAGE_MLP);
         k_mlp<<<grid_for(n, MLP_TILE, sm), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[p], p, h->fdev.latent_index,
                                                                       w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
     }
     NVR_CHECK(h, cudaGetLastError());
-    h->launches += 2 + 2 * NVR_NUM_PARTS;
+    h->launches += 3 + 2 * NVR_NUM_PARTS;
     h->last_points = n;
     return 0;
 }
@@ -360,7 +382,7 @@ extern "C" int nvr_deformer_residual(NvrHandle h, const float* tpts, int64_t n, 
     if (int rc = ready(h, "nvr_deformer_residual")) return rc;
     if (n > 0 && (!tpts || !resd)) return fail(h, "nvr_deformer_residual: null argument");
     if (n == 0) return 0;
-    k_deformer<<<grid_for(n, 128, h->sm_count * 8), 128, 0, (cudaStream_t)stream_>>>(h->fdev, h->def_grid, h->def_mlp, tpts, n, resd);
+    k_deformer<<<grid_for(n, WARP_THREADS, h->sm_count * 4), WARP_THREADS, 0, (cudaStream_t)stream_>>>(h->fdev, h->def_grid, h->def_mlp, tpts, n, resd);
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return 0;
@@ -373,7 +395,7 @@ extern "C" int nvr_embed_part(NvrHandle h, int32_t part, const float* xyz, int64
     if (n == 0) return 0;
     if (n >= (1ll << 31)) return fail(h, "nvr_embed_part: n must be < 2^31");
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
-    k_embed<<<grid_for(n, 64, h->sm_count * 8), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
+    k_embed<<<grid_for(n, 128, h->sm_count * 2), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return 0;

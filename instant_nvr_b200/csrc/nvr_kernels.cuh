@@ -2,8 +2,10 @@
 //
 //   k_frame_prep   per frame: distance channel of pbw -> compact volume, part vertices -> packed float4
 //   k_cull         sample gen (ray mode) / point fetch, world->pose, distance cull, block compaction
-//   k_warp         per survivor: 5x exact K=4 NN, Gaussian blend weights, LBS to big pose, deformer,
-//                  per-part append of flagged (sample, part) pairs
+//   k_cluster_verts per frame: Morton-sorted vertex clusters + AABBs (the KNN acceleration structure)
+//   k_knn          per survivor: 5x exact K=4 NN (group search over the clusters), Gaussian weights,
+//                  per-part append of flagged (sample, part) neighbour records
+//   k_warp         per flagged pair: blend weights, LBS to big pose, deformer -> canonical point + dir
 //   k_embed        THE gather: quad-lane 64-byte row loads of the dense+hashed grids, per-level sums
 //   k_mlp          occ + rgb MLPs on 128-pair tiles (fp32 FFMA register tiles)
 //   k_resolve      arg-max part fusion; per-sample raw/occ and/or per-ray alpha compositing
@@ -32,8 +34,10 @@ struct FrameDev {                  // per-frame tensors as the kernels see them
     const float* Th;
     VolumeDev dist;                // compact (D,H,W,1) distance volume
     VolumeDev tuv;                 // (D',H',W',2)
-    const float4* verts;           // packed part vertices
-    const int* part_off;           // [6] offsets into verts (device)
+    const float4* verts;           // part vertices, spatially sorted, NVR_CL per cluster (x, y, z, orig index)
+    const float4* cl_lo;           // per-cluster AABB
+    const float4* cl_hi;
+    const int* cl_off;             // [6] cluster offsets per part (device)
     const float* part_pbw;         // (P, maxlen, 24)
     int maxlen;
     const float* A;
@@ -54,25 +58,173 @@ struct PartMlpDev {
 // -----------------------------------------------------------------------------------------
 // per-frame preparation
 // -----------------------------------------------------------------------------------------
-__global__ void k_frame_prep(const float* __restrict__ pbw, int n_vox, int C, float* __restrict__ dist,
-                             const float* __restrict__ part_pts, const long long* __restrict__ lengths2,
-                             int maxlen, float4* __restrict__ verts, int* __restrict__ part_off) {
-    int off[NVR_PARTS + 1];
-    off[0] = 0;
-#pragma unroll
+__global__ void k_frame_prep(const float* __restrict__ pbw, int n_vox, int C, float* __restrict__ dist) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid; i < n_vox; i += nth) dist[i] = pbw[(long long)i * C + (C - 1)];
+}
+
+// Per-frame KNN acceleration structure, one CTA per part: sort the part's posed vertices along a
+// 30-bit Morton curve over the part's bounding box (bitonic sort of (code << 32 | index) keys in
+// shared memory), cut the sorted run into clusters of NVR_CL vertices and record each cluster's
+// AABB.  The search in k_warp stays EXACT: clusters are only skipped when their AABB lower bound
+// exceeds the current 4th-best distance.  Padding vertices are +inf (never selected).
+#define NVR_SORT_MAX 8192
+__global__ void __launch_bounds__(1024)
+k_cluster_verts(const float* __restrict__ part_pts, const long long* __restrict__ lengths2, int maxlen,
+                float4* __restrict__ verts, float4* __restrict__ cl_lo, float4* __restrict__ cl_hi,
+                int* __restrict__ cl_off) {
+    extern __shared__ unsigned long long s_key[];
+    __shared__ float s_red[6][32];
+    __shared__ float s_box[6];
+    const int part = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int coff = 0, n = 0;
     for (int p = 0; p < NVR_PARTS; ++p) {
         long long len = lengths2[p];
         len = len < 0 ? 0 : (len > maxlen ? maxlen : len);
-        off[p + 1] = off[p] + (int)len;
+        if (p == part) n = (int)len;
+        if (p < part) coff += (int)((len + NVR_CL - 1) / NVR_CL);
     }
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    if (tid <= NVR_PARTS) part_off[tid] = off[tid];
-    for (int i = tid; i < n_vox; i += nth) dist[i] = pbw[(long long)i * C + (C - 1)];
-    for (int i = tid; i < NVR_PARTS * maxlen; i += nth) {
-        const int p = i / maxlen, j = i - p * maxlen;
-        if (j < off[p + 1] - off[p]) {
-            const float* s = part_pts + (long long)i * 3;
-            verts[off[p] + j] = make_float4(s[0], s[1], s[2], 0.0f);
+    if (tid == 0) cl_off[part + 1] = coff + (n + NVR_CL - 1) / NVR_CL;
+    if (part == 0 && tid == 0) cl_off[0] = 0;
+    const float* src = part_pts + (long long)part * maxlen * 3;
+    // bounding box of the part
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int j = tid; j < n; j += blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float v = src[j * 3 + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+        }
+        if (lane == 0) { s_red[a][wid] = lo[a]; s_red[3 + a][wid] = hi[a]; }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float r = s_red[tid][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = tid < 3 ? fminf(r, s_red[tid][w]) : fmaxf(r, s_red[tid][w]);
+        s_box[tid] = r;
+    }
+    __syncthreads();
+    int M = 32;
+    while (M < n) M <<= 1;
+    for (int j = tid; j < M; j += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (j < n) {
+            unsigned code = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float ext = s_box[3 + a] - s_box[a];
+                float t = ext > 0.0f ? (src[j * 3 + a] - s_box[a]) / ext : 0.0f;
+                int q = (int)(t * 1024.0f);
+                q = q < 0 ? 0 : (q > 1023 ? 1023 : q);            // NaN coordinates land in cell 0
+                unsigned x = (unsigned)q;                         // spread 10 bits to every third position
+                x = (x | (x << 16)) & 0x030000FFu;
+                x = (x | (x << 8)) & 0x0300F00Fu;
+                x = (x | (x << 4)) & 0x030C30C3u;
+                x = (x | (x << 2)) & 0x09249249u;
+                code |= x << a;
+            }
+            key = ((unsigned long long)code << 32) | (unsigned)j;
+        }
+        s_key[j] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= M; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < M; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_key[i], b = s_key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_key[i] = b; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const int ncl = (n + NVR_CL - 1) / NVR_CL;
+    for (int i = tid; i < ncl * NVR_CL; i += blockDim.x) {
+        float4 v = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0));
+        if (i < n) {
+            const int j = (int)(s_key[i] & 0xffffffffull);
+            v = make_float4(src[j * 3], src[j * 3 + 1], src[j * 3 + 2], __int_as_float(j));
+        }
+        verts[(long long)coff * NVR_CL + i] = v;
+    }
+    for (int c = tid; c < ncl; c += blockDim.x) {
+        float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = c * NVR_CL; i < min(n, (c + 1) * NVR_CL); ++i) {
+            const int j = (int)(s_key[i] & 0xffffffffull);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { const float v = src[j * 3 + a]; bl[a] = fminf(bl[a], v); bh[a] = fmaxf(bh[a], v); }
+        }
+        cl_lo[coff + c] = make_float4(bl[0], bl[1], bl[2], __int_as_float(min(n, (c + 1) * NVR_CL) - c * NVR_CL));
+        cl_hi[coff + c] = make_float4(bh[0], bh[1], bh[2], 0.f);
+    }
+}
+
+// Exact K=4 nearest vertices of one part for the 32 queries of a warp (one per lane), as a GROUP
+// search: the warp's survivors are neighbouring samples of one or two rays, so they share most of
+// their candidate set.  qlo/qhi = AABB of the warp's live queries (warp-uniform).
+//   1. lanes share out the part's clusters: U = min over clusters (>= 4 vertices) of the largest
+//      possible query-to-vertex distance bounds EVERY lane's 4th-nearest distance; the cluster whose
+//      box is nearest to the query box is scanned first by all lanes (tight per-lane bounds early);
+//   2. clusters whose box-to-box lower bound exceeds U are dropped for the whole warp (ballot);
+//   3. each remaining cluster is scanned (whole warp, broadcast loads) only if ANY lane's own AABB
+//      lower bound does not exceed its current 4th-best distance.
+// Nothing is approximated: a cluster is skipped only when it cannot contain a better neighbour.
+__device__ __forceinline__ float box_gap2(const float4& lo, const float4& hi, const float qlo[3], const float qhi[3]) {
+    const float dx = fmaxf(fmaxf(lo.x - qhi[0], qlo[0] - hi.x), 0.0f);
+    const float dy = fmaxf(fmaxf(lo.y - qhi[1], qlo[1] - hi.y), 0.0f);
+    const float dz = fmaxf(fmaxf(lo.z - qhi[2], qlo[2] - hi.z), 0.0f);
+    return dx * dx + dy * dy + dz * dz;
+}
+__device__ __forceinline__ float box_reach2(const float4& lo, const float4& hi, const float qlo[3], const float qhi[3]) {
+    const float dx = fmaxf(fabsf(qhi[0] - lo.x), fabsf(hi.x - qlo[0]));
+    const float dy = fmaxf(fabsf(qhi[1] - lo.y), fabsf(hi.y - qlo[1]));
+    const float dz = fmaxf(fabsf(qhi[2] - lo.z), fabsf(hi.z - qlo[2]));
+    return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ void knn_part_group(const FrameDev& fr, int part, const float p[3], bool live,
+                                               const float qlo[3], const float qhi[3], Knn4& k) {
+    const int lane = threadIdx.x & 31;
+    const int c0 = fr.cl_off[part], ncl = fr.cl_off[part + 1] - c0;
+    if (ncl <= 0) return;
+    float U = INFINITY, best = INFINITY;
+    int seed = 0;
+    for (int c = lane; c < ncl; c += 32) {
+        const float4 lo = __ldg(fr.cl_lo + c0 + c), hi = __ldg(fr.cl_hi + c0 + c);
+        if (__float_as_int(lo.w) >= NVR_KNN) U = fminf(U, box_reach2(lo, hi, qlo, qhi));
+        const float g = box_gap2(lo, hi, qlo, qhi);
+        if (g < best) { best = g; seed = c; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        U = fminf(U, __shfl_xor_sync(0xffffffffu, U, d));
+        const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int os = __shfl_xor_sync(0xffffffffu, seed, d);
+        if (ob < best || (ob == best && os < seed)) { best = ob; seed = os; }
+    }
+    U *= 1.00001f;
+    // round -1 holds only the seed (every live lane scans it: k.d2[3] is still +inf); rounds 0.. hold the rest
+    for (int cb = -32; cb < ncl; cb += 32) {
+        const int c = cb + lane;
+        bool cand = lane == 0;
+        if (cb >= 0) {
+            cand = false;
+            if (c < ncl && c != seed)
+                cand = !(box_gap2(__ldg(fr.cl_lo + c0 + c), __ldg(fr.cl_hi + c0 + c), qlo, qhi) * NVR_PRUNE_SLACK > U);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, cand);
+        while (m) {
+            const int cc = cb < 0 ? seed : cb + __ffs(m) - 1;
+            m &= m - 1;
+            const float lb = nvr_aabb_lb(__ldg(fr.cl_lo + c0 + cc), __ldg(fr.cl_hi + c0 + cc), p);
+            const bool need = live && !(lb * NVR_PRUNE_SLACK > k.d2[3]);
+            if (__any_sync(0xffffffffu, need)) nvr_knn_scan(fr.verts + (long long)(c0 + cc) * NVR_CL, NVR_CL, p, k);
         }
     }
 }
@@ -132,150 +284,242 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
 }
 
 // -----------------------------------------------------------------------------------------
-// warp: survivors -> flagged (sample, part) pairs in canonical space
+// knn: survivors -> flagged (sample, part) neighbour records
 // -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs, int dir_div, float thresh,
-       int* __restrict__ counters, const float4* __restrict__ surv, PairRec* __restrict__ pairs, int cap,
-       float4* __restrict__ raws, float* __restrict__ dbg) {
+struct __align__(16) KnnRec {      // a flagged (sample, part) pair before the warp: 48 B
+    float w[NVR_KNN];              // normalised Gaussian weights of the 4 neighbours
+    int idx[NVR_KNN];              // their rows in part_pbw
+    int surv;                      // survivor slot
+    int _pad[3];
+};
+
+__global__ void __launch_bounds__(256)
+k_knn(FrameDev fr, float thresh, int* __restrict__ counters, const float4* __restrict__ surv,
+      KnnRec* __restrict__ recs, int cap, float4* __restrict__ raws, float* __restrict__ dbg) {
     // dbg (optional, per SAMPLE): [n][5][8] = flag, x, y, z, vx, vy, vz, pdist -- per-stage parity tests
-    // deformer MLP weights + both joint transform sets staged once per CTA
-    __shared__ float s_w[32 * 19 + 32 + 32 * 32 + 32 + 3 * 32 + 3 + 1];
-    __shared__ float s_A[NVR_JOINTS * 16], s_bigA[NVR_JOINTS * 16];
-    float* sw0 = s_w; float* sb0 = sw0 + 32 * 19; float* sw1 = sb0 + 32; float* sb1 = sw1 + 32 * 32;
-    float* sw2 = sb1 + 32; float* sb2 = sw2 + 3 * 32;
-    for (int i = threadIdx.x; i < 32 * 19; i += blockDim.x) sw0[i] = dm_g.w0[i];
-    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) sw1[i] = dm_g.w1[i];
-    for (int i = threadIdx.x; i < 3 * 32; i += blockDim.x) sw2[i] = dm_g.w2[i];
-    if (threadIdx.x < 32) { sb0[threadIdx.x] = dm_g.b0[threadIdx.x]; sb1[threadIdx.x] = dm_g.b1[threadIdx.x]; }
-    if (threadIdx.x < 3) sb2[threadIdx.x] = dm_g.b2[threadIdx.x];
-    for (int i = threadIdx.x; i < NVR_JOINTS * 16; i += blockDim.x) { s_A[i] = fr.A[i]; s_bigA[i] = fr.bigA[i]; }
-    __syncthreads();
-    DeformerMlp dm = {sw0, sb0, sw1, sb1, sw2, sb2};
-    const float frame_dim = fr.frame_dim[0];
     const int n_surv = counters[NVR_CTR_SURV];
     const int lane = threadIdx.x & 31;
     // warp-uniform trip count so the ballots below see full warps
     for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_surv; base += gridDim.x * blockDim.x) {
         const int s = base + lane;
         const bool live = s < n_surv;
-        float p[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+        float p[3] = {0.f, 0.f, 0.f};
+        int sample = 0;
         if (live) {
             const float4 sv = surv[s];
             p[0] = sv.x; p[1] = sv.y; p[2] = sv.z;
-            const long long di = (long long)(__float_as_int(sv.w) / dir_div) * 3;
-            const float wd[3] = {dirs[di], dirs[di + 1], dirs[di + 2]};
-            nvr_dir_to_pose(fr.R, wd, d);
+            sample = __float_as_int(sv.w);
+        }
+        float qlo[3], qhi[3];                                     // AABB of the warp's live queries
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            qlo[a] = live ? p[a] : INFINITY;
+            qhi[a] = live ? p[a] : -INFINITY;
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) {
+                qlo[a] = fminf(qlo[a], __shfl_xor_sync(0xffffffffu, qlo[a], dd));
+                qhi[a] = fmaxf(qhi[a], __shfl_xor_sync(0xffffffffu, qhi[a], dd));
+            }
         }
 #pragma unroll 1
         for (int part = 0; part < NVR_PARTS; ++part) {
-            const int off = fr.part_off[part], cnt = fr.part_off[part + 1] - off;
+            Knn4 k;
+            nvr_knn_init(k);
+            knn_part_group(fr, part, p, live, qlo, qhi, k);
             bool flag = false;
-            PairRec rec;
+            KnnRec rec;
             if (live) {
-                Knn4 k;
-                nvr_knn_init(k);
-                nvr_knn_scan(fr.verts + off, cnt, p, k);
-                float bw[NVR_JOINTS];
-                const float pdist = nvr_knn_blend(k, fr.part_pbw + (long long)part * fr.maxlen * NVR_JOINTS, bw);
+                const float pdist = nvr_knn_weights(k, rec.w);
                 flag = pdist < thresh;                             // inb_part_network_multiassign.py:90
-                float* dr = dbg ? dbg + ((long long)__float_as_int(surv[s].w) * NVR_PARTS + part) * 8 : nullptr;
-                if (dr) { dr[0] = flag ? 1.0f : 0.0f; dr[7] = pdist; }
-                if (flag) {
-                    float x0[3], v[3], r[3];
-                    nvr_lbs_to_bigpose(bw, s_A, s_bigA, p, d, x0, v);
-                    nvr_deformer_point(dg, dm, fr.tuv, frame_dim, x0, r);
-                    rec.x = x0[0] + r[0]; rec.y = x0[1] + r[1]; rec.z = x0[2] + r[2];   // :113
-                    rec.vx = v[0]; rec.vy = v[1]; rec.vz = v[2];
-                    rec.surv = s; rec._pad = 0;
-                    if (dr) { dr[1] = rec.x; dr[2] = rec.y; dr[3] = rec.z; dr[4] = v[0]; dr[5] = v[1]; dr[6] = v[2]; }
-                } else {
-                    raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, 0.f);   // :201-202
+                if (dbg) {
+                    float* dr = dbg + ((long long)sample * NVR_PARTS + part) * 8;
+                    dr[0] = flag ? 1.0f : 0.0f; dr[7] = pdist;
                 }
+                if (!flag) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, 0.f);   // :201-202
             }
             const unsigned ballot = __ballot_sync(0xffffffffu, flag);
             if (ballot) {
                 int wbase = 0;
                 if (lane == 0) wbase = atomicAdd(&counters[NVR_CTR_PAIR + part], __popc(ballot));
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (flag) pairs[(long long)part * cap + wbase + __popc(ballot & ((1u << lane) - 1u))] = rec;
+                if (flag) {
+#pragma unroll
+                    for (int i = 0; i < NVR_KNN; ++i) rec.idx[i] = k.idx[i];
+                    rec.surv = s; rec._pad[0] = rec._pad[1] = rec._pad[2] = 0;
+                    recs[(long long)part * cap + wbase + __popc(ballot & ((1u << lane) - 1u))] = rec;
+                }
             }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// warp: neighbour records -> canonical-space pairs (blend, LBS, deformer); blockIdx.y = part
+// -----------------------------------------------------------------------------------------
+#define WARP_THREADS 128
+#define WARP_SMEM_FLOATS (32 * 19 + 32 + 32 * 32 + 32 + 3 * 32 + 4 + 2 * NVR_JOINTS * 16 + 32 * WARP_THREADS)
+struct DeformerSmem { DeformerMlp dm; float* A; float* bigA; float* scratch; };
+__device__ __forceinline__ DeformerSmem stage_deformer(float* sm, const DeformerMlp& g, const float* A, const float* bigA) {
+    float* sw0 = sm; float* sb0 = sw0 + 32 * 19; float* sw1 = sb0 + 32; float* sb1 = sw1 + 32 * 32;
+    float* sw2 = sb1 + 32; float* sb2 = sw2 + 3 * 32; float* sA = sb2 + 4; float* sB = sA + NVR_JOINTS * 16;
+    for (int i = threadIdx.x; i < 32 * 19; i += blockDim.x) sw0[i] = g.w0[i];
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) sw1[i] = g.w1[i];
+    for (int i = threadIdx.x; i < 3 * 32; i += blockDim.x) sw2[i] = g.w2[i];
+    if (threadIdx.x < 32) { sb0[threadIdx.x] = g.b0[threadIdx.x]; sb1[threadIdx.x] = g.b1[threadIdx.x]; }
+    if (threadIdx.x < 3) sb2[threadIdx.x] = g.b2[threadIdx.x];
+    if (A) for (int i = threadIdx.x; i < NVR_JOINTS * 16; i += blockDim.x) { sA[i] = A[i]; sB[i] = bigA[i]; }
+    __syncthreads();
+    DeformerSmem d;
+    d.dm = DeformerMlp{sw0, sb0, sw1, sb1, sw2, sb2};
+    d.A = sA; d.bigA = sB; d.scratch = sB + NVR_JOINTS * 16;
+    return d;
+}
+
+__global__ void __launch_bounds__(WARP_THREADS)
+k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs, int dir_div,
+       const int* __restrict__ counters, const float4* __restrict__ surv, const KnnRec* __restrict__ recs,
+       PairRec* __restrict__ pairs, int cap, float* __restrict__ dbg) {
+    __shared__ __align__(16) float sm[WARP_SMEM_FLOATS];
+    const int part = blockIdx.y;
+    const int n = counters[NVR_CTR_PAIR + part];
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;              // block-uniform
+    const DeformerSmem ds = stage_deformer(sm, dm_g, fr.A, fr.bigA);
+    float* sc = ds.scratch + threadIdx.x;
+    const float frame_dim = fr.frame_dim[0];
+    const float* pbw_part = fr.part_pbw + (long long)part * fr.maxlen * NVR_JOINTS;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const KnnRec rec = recs[(long long)part * cap + i];
+        const float4 sv = surv[rec.surv];
+        const float p[3] = {sv.x, sv.y, sv.z};
+        const int sample = __float_as_int(sv.w);
+        const long long di = (long long)(sample / dir_div) * 3;
+        const float wd[3] = {dirs[di], dirs[di + 1], dirs[di + 2]};
+        float d[3], x0[3], v[3], r[3];
+        nvr_dir_to_pose(fr.R, wd, d);
+        nvr_blend_lbs(rec.idx, rec.w, pbw_part, ds.A, ds.bigA, p, d, x0, v);
+        nvr_deformer_point(dg, ds.dm, fr.tuv, frame_dim, x0, r, sc, WARP_THREADS);
+        PairRec out;
+        out.x = x0[0] + r[0]; out.y = x0[1] + r[1]; out.z = x0[2] + r[2];   // :113
+        out.vx = v[0]; out.vy = v[1]; out.vz = v[2];
+        out.surv = rec.surv; out._pad = 0;
+        pairs[(long long)part * cap + i] = out;
+        if (dbg) {
+            float* dr = dbg + ((long long)sample * NVR_PARTS + part) * 8;
+            dr[1] = out.x; dr[2] = out.y; dr[3] = out.z; dr[4] = v[0]; dr[5] = v[1]; dr[6] = v[2];
         }
     }
 }
 
 // Deformer on explicit canonical points (Network.resd).
-__global__ void k_deformer(FrameDev fr, GridDev dg, DeformerMlp dm, const float* __restrict__ x, long long n,
-                           float* __restrict__ out) {
+__global__ void __launch_bounds__(WARP_THREADS)
+k_deformer(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ x, long long n, float* __restrict__ out) {
+    __shared__ __align__(16) float sm[WARP_SMEM_FLOATS];
+    const DeformerSmem ds = stage_deformer(sm, dm_g, nullptr, nullptr);
+    float* sc = ds.scratch + threadIdx.x;
     const float frame_dim = fr.frame_dim[0];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float x0[3] = {x[i * 3], x[i * 3 + 1], x[i * 3 + 2]};
         float r[3];
-        nvr_deformer_point(dg, dm, fr.tuv, frame_dim, x0, r);
+        nvr_deformer_point(dg, ds.dm, fr.tuv, frame_dim, x0, r, sc, WARP_THREADS);
         out[i * 3] = r[0]; out[i * 3 + 1] = r[1]; out[i * 3 + 2] = r[2];
     }
 }
 
 // -----------------------------------------------------------------------------------------
-// THE gather: part grid embedding, 4 lanes per 64-byte row
+// THE gather: part grid embedding, one 32-byte sector per lane
 // -----------------------------------------------------------------------------------------
-// A warp works on 8 points at a time: lane = 4*point + quarter.  For every level the 8 corner rows
-// (16 fp32 = 64 B each) are fetched as one 16-byte vector per lane, so each warp-wide load
-// instruction covers 8 complete rows = 16 fully-used 32-byte sectors.  Per-feature trilinear sums
-// are kept per lane, folded over the lane's 4 features and then over the 4 quarter-lanes.
+// A warp works on 16 points at a time: lane = 2*point + half.  A grid entry is one 64-byte row of 16
+// fp32 features = two 32-byte sectors; each lane fetches ONE whole sector with a single 256-bit load
+// (LDG.E.256), so every byte of every sector that moves is used and the per-point index arithmetic is
+// shared by only two lanes.  The 8 corner loads of a level are independent and issued back to back.
+// The level loop is deliberately NOT unrolled: unrolled, the kernel is ~10k instructions and spends
+// most of its time waiting for instruction fetch (profiles/r1a: 62 % stall_no_inst); rolled it is a
+// few hundred instructions that stay in the instruction cache.
 // Input points: float x[3] at `xbase + i * xstride` (PairRec lists: stride 8; plain xyz: stride 3).
 // The point count is *count_dev when non-null (device-side list length), else n_imm.  One launch per part.
-__device__ __forceinline__ float4 ld_row_quarter(const float* tab, long long row, int q) {
-    return __ldg(reinterpret_cast<const float4*>(tab + row * 16) + q);
+struct __align__(32) Sector { float v[8]; };
+__device__ __forceinline__ Sector ld_sector(const float* p) {
+    Sector r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
 }
 
-__global__ void __launch_bounds__(256)
+// Clamped corner coordinates of one axis, reference semantics (part_base_embedder.py:115-118):
+// `.long()` truncates toward zero; cvt.rzi.s32 saturates instead of wrapping, which is the same after
+// the clamp to [0, res-1] (NaN -> 0 -> clamps to 0, as LLONG_MIN does).
+__device__ __forceinline__ void axis_coord(float u, float size, int res, int& i0, int& i1, float& o) {
+    const float f = u / size;                                     // IEEE fp32 divide
+    i0 = min(max(__float2int_rz(f + 0.0f), 0), res - 1);
+    i1 = min(max(__float2int_rz(f + 1.0f), 0), res - 1);
+    o = f - (float)i0;
+}
+
+__global__ void __launch_bounds__(256, 2)
 k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
         float* __restrict__ eb, int emb_stride) {
     const int n = count_dev ? *count_dev : n_imm;
-    const int lane = threadIdx.x & 31, q = lane & 3;
+    const int lane = threadIdx.x & 31, half = lane & 1;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int base = warp * 8; base < n; base += n_warps * 8) {
-        const int pt = base + (lane >> 2);
+    const bool fast_mod = g.T_magic40 != 0;
+    const unsigned int T32 = (unsigned int)g.T;
+    for (int base = warp * 16; base < n; base += n_warps * 16) {
+        const int pt = base + (lane >> 1);
         const bool live = pt < n;
-        const int pi = live ? pt : n - 1;
-        const float* xp = xb + (long long)pi * xstride;
+        const float* xp = xb + (long long)(live ? pt : n - 1) * xstride;
         const float x[3] = {xp[0], xp[1], xp[2]};
         float u[3];
         nvr_normalise(g, x, u);
-        float lev[NVR_LEVELS];
+        float* o = eb + (long long)pt * emb_stride;
+        if (live && half == 0) { o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; }
+#pragma unroll 1
+        for (int l = 0; l < g.n_levels; ++l) {
+            const int res = g.res[l];
+            const float size = g.size[l];
+            int i0[3], i1[3];
+            float of[3];
 #pragma unroll
-        for (int l = 0; l < NVR_LEVELS; ++l) {
-            lev[l] = 0.0f;
-            if (l < g.n_levels) {
-                LevelCoord lc;
-                nvr_level_coord(u, g.size[l], g.res[l], lc);
-                const float* tab = nvr_level_table(g, l);
-                float4 v[8];
-                float w[8];
+            for (int a = 0; a < 3; ++a) axis_coord(u[a], size, res, i0[a], i1[a], of[a]);
+            // per-axis contributions to the row index, then 8 corner rows (x = bit 2, y = bit 1, z = bit 0)
+            unsigned int row[8];
+            const float* tab;
+            if (l < g.start_hash) {                               // dense level  (:124-129)
+                tab = g.dense;
+                const unsigned int off = (unsigned int)g.dense_off[l];
+                const unsigned int ax[2] = {(unsigned int)(i0[0] * res * res) + off, (unsigned int)(i1[0] * res * res) + off};
+                const unsigned int ay[2] = {(unsigned int)(i0[1] * res), (unsigned int)(i1[1] * res)};
+                const unsigned int az[2] = {(unsigned int)i0[2], (unsigned int)i1[2]};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) row[c] = ax[(c >> 2) & 1] + ay[(c >> 1) & 1] + az[c & 1];
+            } else {                                              // hashed level (:132-136), int64 products
+                tab = g.hash;
+                const unsigned int off = (unsigned int)(l - g.start_hash) * T32;
+                const unsigned long long hx[2] = {(unsigned long long)i0[0], (unsigned long long)i1[0]};
+                const unsigned long long hy[2] = {(unsigned long long)i0[1] * 19349663ull, (unsigned long long)i1[1] * 19349663ull};
+                const unsigned long long hz[2] = {(unsigned long long)i0[2] * 83492791ull, (unsigned long long)i1[2] * 83492791ull};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    v[c] = ld_row_quarter(tab, nvr_corner_row(g, l, lc, c), q);
-                    w[c] = nvr_corner_weight(lc, c);
+                    const unsigned long long h = hx[(c >> 2) & 1] ^ hy[(c >> 1) & 1] ^ hz[c & 1];
+                    row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
                 }
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    a.x += w[c] * v[c].x; a.y += w[c] * v[c].y; a.z += w[c] * v[c].z; a.w += w[c] * v[c].w;
-                }
-                float s = (a.x + a.y) + (a.z + a.w);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                lev[l] = s;
             }
-        }
-        if (live) {
-            float* o = eb + (long long)pt * emb_stride;
-            // element e is written by quarter-lane e % 4
+            Sector v[8];
 #pragma unroll
-            for (int e = 0; e < 19; ++e) {
-                if ((e & 3) == q) o[e] = e < 3 ? u[e] : lev[e - 3];
+            for (int c = 0; c < 8; ++c) v[c] = ld_sector(tab + (unsigned long long)row[c] * 16 + half * 8);
+            const float wx[2] = {1.0f - of[0], of[0]}, wy[2] = {1.0f - of[1], of[1]}, wz[2] = {1.0f - of[2], of[2]};
+            float acc[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[f] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float w = (wx[(c >> 2) & 1] * wy[(c >> 1) & 1]) * wz[c & 1];      // :158-159
+#pragma unroll
+                for (int f = 0; f < 8; ++f) acc[f] += w * v[c].v[f];                    // :160
             }
+            float sfeat = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            sfeat += __shfl_xor_sync(0xffffffffu, sfeat, 1);                            // :165 sum over the 16 features
+            if (live && half == (l & 1)) o[3 + l] = sfeat;
         }
     }
 }

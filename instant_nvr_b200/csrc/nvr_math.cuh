@@ -9,6 +9,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define NVR_HD __host__ __device__ __forceinline__
@@ -30,6 +31,7 @@ struct GridDev {
     int n_levels, n_feat, start_hash, sum_features;
     unsigned long long T;
     unsigned long long T_magic;   // floor(2^64 / T)
+    unsigned int T_magic40;       // floor(2^40 / T); 0 when the 32-bit reduction is not applicable (see nvr_mod_T40)
     int res[NVR_LEVELS];
     float size[NVR_LEVELS];
     long long dense_off[NVR_LEVELS];
@@ -62,6 +64,27 @@ NVR_HD unsigned long long nvr_mod_T(unsigned long long h, unsigned long long T, 
     unsigned long long q = nvr_umulhi64(h, magic);
     unsigned long long r = h - q * T;
     return r >= T ? r - T : r;
+}
+
+// h mod T for h < 2^40 and 2^8 < T < 2^31 with 32-bit arithmetic: q = umulhi(h >> 8, floor(2^40 / T))
+// under-estimates floor(h / T) by at most 1 (h / 2^40 + 2^8 / T < 1), so two conditional subtractions
+// are more than enough.  The part grids satisfy the bounds: coordinates < 2^13 make the int64 hash
+// (x*1 ^ y*19349663 ^ z*83492791) < 2^40.  tests/test_host_emul.py::test_barrett_mod checks it against %.
+NVR_HD unsigned int nvr_umulhi32(unsigned int a, unsigned int b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (unsigned int)(((unsigned long long)a * b) >> 32);
+#endif
+}
+NVR_HD unsigned int nvr_mod_T40(unsigned long long h, unsigned int T, unsigned int magic40) {
+    const unsigned int q = nvr_umulhi32((unsigned int)(h >> 8), magic40);
+    unsigned int r = (unsigned int)h - q * T;                    // exact modulo 2^32, true value < 3T
+    unsigned int t = r - T;
+    r = t < r ? t : r;                                           // r >= T  <=>  r - T does not wrap
+    t = r - T;
+    r = t < r ? t : r;
+    return r;
 }
 
 struct LevelCoord {
@@ -119,10 +142,10 @@ NVR_HD void nvr_normalise(const GridDev& g, const float x[3], float u[3]) {
 // which shares nvr_level_coord / nvr_corner_row / nvr_corner_weight with this function.
 //   sum_features: out[3 + l] = sum_f sum_c w_c * t[row_c][f];  concat: out[3 + l*F + f]
 template <int F>
-NVR_HD void nvr_embed_point(const GridDev& g, const float x[3], float* out) {
+NVR_HD void nvr_embed_point(const GridDev& g, const float x[3], float* out, int os = 1) {   // os: output element stride
     float u[3];
     nvr_normalise(g, x, u);
-    out[0] = u[0]; out[1] = u[1]; out[2] = u[2];
+    out[0] = u[0]; out[os] = u[1]; out[2 * os] = u[2];
     for (int l = 0; l < g.n_levels; ++l) {
         LevelCoord lc;
         nvr_level_coord(u, g.size[l], g.res[l], lc);
@@ -141,10 +164,10 @@ NVR_HD void nvr_embed_point(const GridDev& g, const float x[3], float* out) {
             float s = 0.0f;
 #pragma unroll
             for (int f = 0; f < F; ++f) s += acc[f];                            // :165
-            out[3 + l] = s;
+            out[(3 + l) * os] = s;
         } else {
 #pragma unroll
-            for (int f = 0; f < F; ++f) out[3 + l * F + f] = acc[f];            // :169
+            for (int f = 0; f < F; ++f) out[(3 + l * F + f) * os] = acc[f];     // :169
         }
     }
 }
@@ -196,14 +219,17 @@ NVR_HD void nvr_knn_init(Knn4& k) {
 #pragma unroll
     for (int i = 0; i < NVR_KNN; ++i) { k.d2[i] = INFINITY; k.idx[i] = 0; }
 }
-// insert keeping ascending order; ties keep the earlier index first (what a stable top-k does)
+// Candidates are ordered by (d2, vertex index): the result does not depend on the order in which
+// vertices are visited, and equals a stable top-k over the original vertex order (ties keep the
+// lower index).  That freedom is what lets the production scan walk spatially sorted clusters.
+NVR_HD bool nvr_knn_less(float d2a, int ja, float d2b, int jb) { return d2a < d2b || (d2a == d2b && ja < jb); }
 NVR_HD void nvr_knn_insert(Knn4& k, float d2, int j) {
-    if (d2 < k.d2[3]) {
-        if (d2 < k.d2[2]) {
+    if (nvr_knn_less(d2, j, k.d2[3], k.idx[3])) {
+        if (nvr_knn_less(d2, j, k.d2[2], k.idx[2])) {
             k.d2[3] = k.d2[2]; k.idx[3] = k.idx[2];
-            if (d2 < k.d2[1]) {
+            if (nvr_knn_less(d2, j, k.d2[1], k.idx[1])) {
                 k.d2[2] = k.d2[1]; k.idx[2] = k.idx[1];
-                if (d2 < k.d2[0]) {
+                if (nvr_knn_less(d2, j, k.d2[0], k.idx[0])) {
                     k.d2[1] = k.d2[0]; k.idx[1] = k.idx[0];
                     k.d2[0] = d2; k.idx[0] = j;
                 } else { k.d2[1] = d2; k.idx[1] = j; }
@@ -212,24 +238,75 @@ NVR_HD void nvr_knn_insert(Knn4& k, float d2, int j) {
     }
 }
 
-// verts: packed float4 (x,y,z,_) of ONE part, `count` of them.  Exact brute force.
-NVR_HD void nvr_knn_scan(const float4* verts, int count, const float p[3], Knn4& k) {
-    for (int j = 0; j < count; ++j) {
+NVR_HD float nvr_dist2(const float p[3], const float4& v) {
+    const float dx = p[0] - v.x, dy = p[1] - v.y, dz = p[2] - v.z;
+    return dx * dx + dy * dy + dz * dz;                           // squared L2, as knn_points returns it
+}
+
+NVR_HD float4 nvr_ld_vert(const float4* v) {
 #ifdef __CUDA_ARCH__
-        const float4 v = __ldg(verts + j);
+    return __ldg(v);
 #else
-        const float4 v = verts[j];
+    return *v;
 #endif
-        const float dx = p[0] - v.x, dy = p[1] - v.y, dz = p[2] - v.z;
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        nvr_knn_insert(k, d2, j);
+}
+NVR_HD int nvr_vert_id(const float4& v) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(v.w);
+#else
+    int id; memcpy(&id, &v.w, 4); return id;
+#endif
+}
+
+// verts: (x, y, z, bit pattern of the ORIGINAL vertex index) of one run of vertices.  Exact.
+// Vertices are taken four at a time: the common case (none of the four beats the current 4th-best)
+// costs the distance arithmetic plus one compare and one branch.
+NVR_HD void nvr_knn_scan(const float4* verts, int count, const float p[3], Knn4& k) {
+    int j = 0;
+#pragma unroll 2
+    for (; j + 4 <= count; j += 4) {
+        const float da = nvr_dist2(p, nvr_ld_vert(verts + j)), db = nvr_dist2(p, nvr_ld_vert(verts + j + 1)),
+                    dc = nvr_dist2(p, nvr_ld_vert(verts + j + 2)), dd = nvr_dist2(p, nvr_ld_vert(verts + j + 3));
+        if (fminf(fminf(da, db), fminf(dc, dd)) <= k.d2[3]) {
+            // rare path, kept rolled (one insertion site): re-read the four vertices one by one
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = nvr_ld_vert(verts + j + q);
+                const float d2 = nvr_dist2(p, v);
+                if (d2 <= k.d2[3]) nvr_knn_insert(k, d2, nvr_vert_id(v));
+            }
+        }
+    }
+#pragma unroll 1
+    for (; j < count; ++j) {
+        const float4 v = nvr_ld_vert(verts + j);
+        const float d2 = nvr_dist2(p, v);
+        if (d2 <= k.d2[3]) nvr_knn_insert(k, d2, nvr_vert_id(v));
     }
 }
 
-// From the 4 neighbours to (bw[24], pdist): sample_blend_closest_points, :741-763.
-// pbw_part: (maxlen, 24) rows of this part.  n_valid < 4 only if the part has < 4 vertices.
-NVR_HD float nvr_knn_blend(const Knn4& k, const float* pbw_part, float bw[NVR_JOINTS]) {
-    float d[NVR_KNN], w[NVR_KNN], wsum = 0.0f;
+// Lower bound of nvr_dist2(p, v) over every v inside the box [lo, hi].  Each fp32 operation in
+// nvr_dist2 is monotone in |p - v| per axis, so the same expression on the per-axis gap is a lower
+// bound up to the contraction (fma vs mul+add) the compiler picks; callers prune with a 1e-6
+// relative slack for that.
+NVR_HD float nvr_aabb_lb(const float4& lo, const float4& hi, const float p[3]) {
+    const float dx = fmaxf(fmaxf(lo.x - p[0], p[0] - hi.x), 0.0f);
+    const float dy = fmaxf(fmaxf(lo.y - p[1], p[1] - hi.y), 0.0f);
+    const float dz = fmaxf(fmaxf(lo.z - p[2], p[2] - hi.z), 0.0f);
+    return dx * dx + dy * dy + dz * dz;
+}
+#ifdef NVR_CL_OVERRIDE
+#define NVR_CL NVR_CL_OVERRIDE
+#else
+#define NVR_CL 32
+#endif
+// vertices per spatial cluster (one AABB each)
+#define NVR_PRUNE_SLACK 0.999999f
+
+// From the 4 neighbours to their normalised Gaussian weights and the weighted distance:
+// sample_blend_closest_points, :741-748.
+NVR_HD float nvr_knn_weights(const Knn4& k, float w[NVR_KNN]) {
+    float d[NVR_KNN], wsum = 0.0f;
 #pragma unroll
     for (int i = 0; i < NVR_KNN; ++i) {
         d[i] = sqrtf(k.d2[i]);                                   // cast_knn_points :736
@@ -243,36 +320,31 @@ NVR_HD float nvr_knn_blend(const Knn4& k, const float* pbw_part, float bw[NVR_JO
         w[i] = w[i] / denom;
         pdist += d[i] * w[i];                                    // :748
     }
+    return pdist;
+}
+
+// Blend weight of joint j from the 4 neighbour rows (:762).  pbw_part: (maxlen, 24) rows of this part.
+NVR_HD float nvr_blend_joint(const int idx[NVR_KNN], const float w[NVR_KNN], const float* pbw_part, int j) {
+    float b = 0.0f;
 #pragma unroll
-    for (int j = 0; j < NVR_JOINTS; ++j) bw[j] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NVR_KNN; ++i) {
-        const float* row = pbw_part + (long long)k.idx[i] * NVR_JOINTS;
-#pragma unroll
-        for (int j = 0; j < NVR_JOINTS; ++j) bw[j] += row[j] * w[i];   // :762
-    }
+    for (int i = 0; i < NVR_KNN; ++i) b += pbw_part[(long long)idx[i] * NVR_JOINTS + j] * w[i];
+    return b;
+}
+
+// (bw[24], pdist) in one call -- host emulation and per-stage tests.
+NVR_HD float nvr_knn_blend(const Knn4& k, const float* pbw_part, float bw[NVR_JOINTS]) {
+    float w[NVR_KNN];
+    const float pdist = nvr_knn_weights(k, w);
+    for (int j = 0; j < NVR_JOINTS; ++j) bw[j] = nvr_blend_joint(k.idx, w, pbw_part, j);
     return pdist;
 }
 
 // ---------------------------------------------------------------------------------------
 // LBS: pose space -> T pose -> big pose             blend_utils.py:293-317, 395-487
 // ---------------------------------------------------------------------------------------
-// A, bigA: (24,4,4) row-major.  In: pose-space point p, direction d, blend weights bw.
+// M, B: rows 0..2 of the blended pose / big-pose 4x4s.  In: pose-space point p, direction d.
 // Out: big-pose point x0 and direction v.
-NVR_HD void nvr_lbs_to_bigpose(const float bw[NVR_JOINTS], const float* A, const float* bigA,
-                               const float p[3], const float d[3], float x0[3], float v[3]) {
-    float M[12], B[12];                                           // rows 0..2 of the blended 4x4s
-#pragma unroll
-    for (int e = 0; e < 12; ++e) { M[e] = 0.0f; B[e] = 0.0f; }
-#pragma unroll
-    for (int j = 0; j < NVR_JOINTS; ++j) {
-        const float w = bw[j];
-#pragma unroll
-        for (int e = 0; e < 12; ++e) {
-            M[e] += w * A[j * 16 + e];                            // get_inverse_blend_params :415
-            B[e] += w * bigA[j * 16 + e];                         // get_blend_params :402
-        }
-    }
+NVR_HD void nvr_lbs_apply(const float M[12], const float B[12], const float p[3], const float d[3], float x0[3], float v[3]) {
     // 3x3 inverse by transposed cofactors / (det + fp32 eps)      torch_inverse_3x3 :293-317
     const float a = M[0], b = M[1], c = M[2], dd = M[4], e = M[5], f = M[6], g = M[8], h = M[9], i = M[10];
     const float m00 = e * i - f * h, m01 = dd * i - f * g, m02 = dd * h - e * g;
@@ -296,6 +368,43 @@ NVR_HD void nvr_lbs_to_bigpose(const float bw[NVR_JOINTS], const float* A, const
         x0[r] = ((B[r * 4 + 0] * t[0] + B[r * 4 + 1] * t[1]) + B[r * 4 + 2] * t[2]) + B[r * 4 + 3];   // :469-470
         v[r] = (B[r * 4 + 0] * td[0] + B[r * 4 + 1] * td[1]) + B[r * 4 + 2] * td[2];                  // :486
     }
+}
+
+// A, bigA: (24,4,4) row-major.  Blend weights given explicitly (host emulation, tests).
+NVR_HD void nvr_lbs_to_bigpose(const float bw[NVR_JOINTS], const float* A, const float* bigA,
+                               const float p[3], const float d[3], float x0[3], float v[3]) {
+    float M[12], B[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) { M[e] = 0.0f; B[e] = 0.0f; }
+    for (int j = 0; j < NVR_JOINTS; ++j) {
+        const float w = bw[j];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            M[e] += w * A[j * 16 + e];                            // get_inverse_blend_params :415
+            B[e] += w * bigA[j * 16 + e];                         // get_blend_params :402
+        }
+    }
+    nvr_lbs_apply(M, B, p, d, x0, v);
+}
+
+// The production form: blend weights are produced joint by joint from the neighbour rows and folded
+// straight into the two blended transforms (same operation order as the two-step form above), so the
+// 24 weights never exist as an array and the joint loop stays rolled (small code, no local memory).
+NVR_HD void nvr_blend_lbs(const int idx[NVR_KNN], const float w[NVR_KNN], const float* pbw_part, const float* A,
+                          const float* bigA, const float p[3], const float d[3], float x0[3], float v[3]) {
+    float M[12], B[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) { M[e] = 0.0f; B[e] = 0.0f; }
+#pragma unroll 2
+    for (int j = 0; j < NVR_JOINTS; ++j) {
+        const float bj = nvr_blend_joint(idx, w, pbw_part, j);
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            M[e] += bj * A[j * 16 + e];
+            B[e] += bj * bigA[j * 16 + e];
+        }
+    }
+    nvr_lbs_apply(M, B, p, d, x0, v);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -323,35 +432,49 @@ struct DeformerMlp {
     const float *w0, *b0, *w1, *b1, *w2, *b2;    // 32x19, 32, 32x32, 32, 3x32, 3
 };
 
+// sc: 32 scratch floats of THIS thread, element stride ss (shared memory on the device: sc = base + tid,
+// ss = block size, so neighbouring lanes hit neighbouring banks; a plain array with ss = 1 on the host).
+// The output loops stay rolled -- the activations live in the scratch row instead of 64 registers --
+// which keeps the kernel's code inside the instruction cache.
 NVR_HD void nvr_deformer_point(const GridDev& g, const DeformerMlp& m, const VolumeDev& tuv, float frame_dim,
-                               const float x0[3], float resd[3]) {
+                               const float x0[3], float resd[3], float* sc, int ss) {
     float uvt[3];
     nvr_sample_volume(tuv, x0, 0, 2, uvt);                        // pts_sample_uv :32
     uvt[2] = frame_dim;                                           // :35
-    float e[19];
-    nvr_embed_point<2>(g, uvt, e);                                // :37 (8 levels x 2 features, concat)
-    float h1[32], h2[32];
+    nvr_embed_point<2>(g, uvt, sc, ss);                           // :37 (8 levels x 2 features, concat) -> sc[0..18]
+    {
+        float e[19];
 #pragma unroll
-    for (int o = 0; o < 32; ++o) {
-        float acc = m.b0[o];
+        for (int i = 0; i < 19; ++i) e[i] = sc[i * ss];
+#pragma unroll 1
+        for (int o = 0; o < 32; ++o) {
+            float acc = m.b0[o];
 #pragma unroll
-        for (int i = 0; i < 19; ++i) acc += m.w0[o * 19 + i] * e[i];
-        h1[o] = nvr_softplus(acc);
+            for (int i = 0; i < 19; ++i) acc += m.w0[o * 19 + i] * e[i];
+            sc[o * ss] = nvr_softplus(acc);
+        }
+    }
+    {
+        float h1[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h1[i] = sc[i * ss];
+#pragma unroll 1
+        for (int o = 0; o < 32; ++o) {
+            float acc = m.b1[o];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += m.w1[o * 32 + i] * h1[i];
+            sc[o * ss] = nvr_softplus(acc);
+        }
+    }
+    float acc[3] = {m.b2[0], m.b2[1], m.b2[2]};
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+        const float h = sc[i * ss];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) acc[o] += m.w2[o * 32 + i] * h;
     }
 #pragma unroll
-    for (int o = 0; o < 32; ++o) {
-        float acc = m.b1[o];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc += m.w1[o * 32 + i] * h1[i];
-        h2[o] = nvr_softplus(acc);
-    }
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-        float acc = m.b2[o];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc += m.w2[o * 32 + i] * h2[i];
-        resd[o] = 0.05f * tanhf(acc);                             // :39
-    }
+    for (int o = 0; o < 3; ++o) resd[o] = 0.05f * tanhf(acc[o]);  // :39
 }
 
 // ---------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 // without a GPU.  Nothing in the product links or loads this file; it is not a CPU fallback.
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/nvr_b200.h"
@@ -37,6 +38,11 @@ long long emul_check_mod(long long T, const long long* h, long long n) {
     long long bad = 0;
     for (long long i = 0; i < n; ++i)
         if (nvr_mod_T((unsigned long long)h[i], (unsigned long long)T, magic) != (unsigned long long)h[i] % (unsigned long long)T) ++bad;
+    // the 32-bit reduction used by the gather kernel, on the values inside its domain (h < 2^40)
+    const unsigned int magic40 = (unsigned int)((1ull << 40) / (unsigned long long)T);
+    for (long long i = 0; i < n; ++i)
+        if ((unsigned long long)h[i] < (1ull << 40) &&
+            nvr_mod_T40((unsigned long long)h[i], (unsigned int)T, magic40) != (unsigned long long)h[i] % (unsigned long long)T) ++bad;
     return bad;
 }
 
@@ -57,20 +63,79 @@ void emul_ray_points(const float* ray_o, const float* ray_d, const float* near_,
         }
 }
 
+// Host restatement of k_cluster_verts (Morton sort over the part bbox, clusters of NVR_CL, AABBs).
+struct HostClusters { std::vector<float4> verts, lo, hi; };
+static float idx_bits(int j) { float f; memcpy(&f, &j, 4); return f; }
+static HostClusters build_clusters(const float* src, int n) {
+    HostClusters hc;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int j = 0; j < n; ++j)
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], src[j * 3 + a]); hi[a] = fmaxf(hi[a], src[j * 3 + a]); }
+    std::vector<unsigned long long> keys(n);
+    for (int j = 0; j < n; ++j) {
+        unsigned code = 0;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = hi[a] - lo[a];
+            float t = ext > 0.0f ? (src[j * 3 + a] - lo[a]) / ext : 0.0f;
+            int q = (int)(t * 1024.0f);
+            q = q < 0 ? 0 : (q > 1023 ? 1023 : q);
+            for (int b = 0; b < 10; ++b) code |= ((unsigned)(q >> b) & 1u) << (3 * b + a);
+        }
+        keys[j] = ((unsigned long long)code << 32) | (unsigned)j;
+    }
+    std::sort(keys.begin(), keys.end());
+    const int ncl = (n + NVR_CL - 1) / NVR_CL;
+    hc.verts.assign((size_t)ncl * NVR_CL, float4{INFINITY, INFINITY, INFINITY, idx_bits(0)});
+    hc.lo.assign(ncl, float4{INFINITY, INFINITY, INFINITY, 0.f});
+    hc.hi.assign(ncl, float4{-INFINITY, -INFINITY, -INFINITY, 0.f});
+    for (int i = 0; i < n; ++i) {
+        const int j = (int)(keys[i] & 0xffffffffull), c = i / NVR_CL;
+        hc.verts[i] = float4{src[j * 3], src[j * 3 + 1], src[j * 3 + 2], idx_bits(j)};
+        hc.lo[c].x = fminf(hc.lo[c].x, src[j * 3]); hc.hi[c].x = fmaxf(hc.hi[c].x, src[j * 3]);
+        hc.lo[c].y = fminf(hc.lo[c].y, src[j * 3 + 1]); hc.hi[c].y = fmaxf(hc.hi[c].y, src[j * 3 + 1]);
+        hc.lo[c].z = fminf(hc.lo[c].z, src[j * 3 + 2]); hc.hi[c].z = fmaxf(hc.hi[c].z, src[j * 3 + 2]);
+    }
+    return hc;
+}
+
 // per point: for each of the 5 parts, K=4 NN blend weights (bw 24, pdist) and the LBS warp (x0, v).
+// clustered = 0: brute force over the vertices in their original order.
+// clustered = 1: the pruned search of k_warp (seed cluster, then AABB lower bounds), scalar form: the
+//                seed is chosen for a DIFFERENT point (the previous one), as lane 0's query is on the GPU.
+// idx_out (optional): the 4 selected vertex indices per (point, part), sorted ascending by (d2, index).
 void emul_knn_lbs(const float* part_pts, const float* part_pbw, const long long* lengths2, int maxlen, const float* A,
                   const float* bigA, const float* pts, const float* dirs, long long n, float* bw_out, float* pdist_out,
-                  float* x0_out, float* v_out) {
+                  float* x0_out, float* v_out, int clustered, int* idx_out, long long* scanned_out) {
+    long long scanned = 0;
     for (int part = 0; part < NVR_PARTS; ++part) {
-        std::vector<float4> verts(lengths2[part]);
-        for (long long j = 0; j < lengths2[part]; ++j) {
-            const float* s = part_pts + ((long long)part * maxlen + j) * 3;
-            verts[j] = float4{s[0], s[1], s[2], 0.f};
-        }
+        const int cnt = (int)lengths2[part];
+        const float* src = part_pts + (long long)part * maxlen * 3;
+        std::vector<float4> verts(cnt);
+        for (int j = 0; j < cnt; ++j) verts[j] = float4{src[j * 3], src[j * 3 + 1], src[j * 3 + 2], idx_bits(j)};
+        HostClusters hc = build_clusters(src, cnt);
+        const int ncl = (int)hc.lo.size();
         for (long long i = 0; i < n; ++i) {
             Knn4 k;
             nvr_knn_init(k);
-            nvr_knn_scan(verts.data(), (int)verts.size(), pts + i * 3, k);
+            const float* p = pts + i * 3;
+            if (!clustered) {
+                nvr_knn_scan(verts.data(), cnt, p, k);
+            } else if (ncl > 0) {
+                const float* rep = clustered == 2 ? p : pts + (i > 0 ? i - 1 : 0) * 3;   // 2: own point (best case)
+                int seed = 0;
+                float best = INFINITY;
+                for (int c = 0; c < ncl; ++c) {
+                    const float lb = nvr_aabb_lb(hc.lo[c], hc.hi[c], rep);
+                    if (lb < best) { best = lb; seed = c; }
+                }
+                nvr_knn_scan(hc.verts.data() + (size_t)seed * NVR_CL, NVR_CL, p, k);
+                ++scanned;
+                for (int c = 0; c < ncl; ++c) {
+                    if (c == seed) continue;
+                    const float lb = nvr_aabb_lb(hc.lo[c], hc.hi[c], p);
+                    if (!(lb * NVR_PRUNE_SLACK > k.d2[3])) { nvr_knn_scan(hc.verts.data() + (size_t)c * NVR_CL, NVR_CL, p, k); ++scanned; }
+                }
+            }
             float bw[NVR_JOINTS];
             float pd = nvr_knn_blend(k, part_pbw + (long long)part * maxlen * NVR_JOINTS, bw);
             float x0[3], v[3];
@@ -79,8 +144,10 @@ void emul_knn_lbs(const float* part_pts, const float* part_pbw, const long long*
             for (int j = 0; j < NVR_JOINTS; ++j) bw_out[o * NVR_JOINTS + j] = bw[j];
             pdist_out[o] = pd;
             for (int a = 0; a < 3; ++a) { x0_out[o * 3 + a] = x0[a]; v_out[o * 3 + a] = v[a]; }
+            if (idx_out) for (int q = 0; q < NVR_KNN; ++q) idx_out[o * NVR_KNN + q] = k.idx[q];
         }
     }
+    if (scanned_out) *scanned_out = scanned;
 }
 
 void emul_deformer(const NvrGrid* g, const NvrLinear* mlp, const float* tuv, int D, int H, int W, const float* tbounds,
@@ -88,7 +155,8 @@ void emul_deformer(const NvrGrid* g, const NvrLinear* mlp, const float* tuv, int
     GridDev d = to_dev(*g);
     DeformerMlp m{mlp[0].weight, mlp[0].bias, mlp[1].weight, mlp[1].bias, mlp[2].weight, mlp[2].bias};
     VolumeDev v{tuv, D, H, W, 2, tbounds};
-    for (long long i = 0; i < n; ++i) nvr_deformer_point(d, m, v, frame_dim, x0 + i * 3, out + i * 3);
+    float sc[32];
+    for (long long i = 0; i < n; ++i) nvr_deformer_point(d, m, v, frame_dim, x0 + i * 3, out + i * 3, sc, 1);
 }
 
 void emul_posenc(const float* v, long long n, float* out) {

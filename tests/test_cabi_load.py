@@ -35,7 +35,10 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version(lib):
-    assert lib.nvr_abi_version() == 1
+    from instant_nvr_b200 import cabi
+    header = open(os.path.join(REPO, "include", "nvr_b200.h")).read()
+    declared = int(re.search(r"#define NVR_ABI_VERSION (\d+)", header).group(1))
+    assert lib.nvr_abi_version() == cabi.ABI_VERSION == declared
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -63,7 +63,8 @@ def test_native_library_is_loaded(gpu):
     eng = gpu["nets"][1.0].engine()
     with open("/proc/self/maps") as f:
         assert "libnvr_b200.so" in f.read()
-    assert eng.lib.nvr_abi_version() == 1
+    from instant_nvr_b200 import cabi
+    assert eng.lib.nvr_abi_version() == cabi.ABI_VERSION
 
 
 def _inside(x, bounds):

@@ -46,10 +46,12 @@ def test_struct_sizes_match_header(emul):
 
 def test_barrett_mod(emul):
     rng = np.random.default_rng(0)
-    for T in (16411, 32771, 65537, 262147, 1048583):
-        ix, iy, iz = (rng.integers(0, 2100, 200000) for _ in range(3))
+    for T in (257, 4099, 16411, 32771, 65537, 262147, 1048583, 2**31 - 1):
+        ix, iy, iz = (rng.integers(0, 8192, 400000) for _ in range(3))
         h = (ix * 1) ^ (iy * 19349663) ^ (iz * 83492791)
-        h = np.concatenate([h, [0, T - 1, T, T + 1, 2 * T - 1, 2**40, 2**62 + 12345]]).astype(np.int64)
+        k = np.arange(1, 4000, dtype=np.int64)
+        edges = np.concatenate([k * T - 1, k * T, k * T + 1, (2**40 // T - k) * T - 1, (2**40 // T - k) * T])
+        h = np.concatenate([h, edges, [0, T - 1, T, T + 1, 2 * T - 1, 2**40 - 1, 2**40, 2**62 + 12345]]).astype(np.int64)
         emul.emul_check_mod.restype = C.c_longlong
         bad = emul.emul_check_mod(C.c_longlong(T), h.ctypes.data_as(C.c_void_p), C.c_longlong(len(h)))
         assert bad == 0, T
@@ -188,8 +190,20 @@ def test_knn_lbs(emul, golden_setup):
     A, bA = frame["A"][0].contiguous(), frame["big_A"][0].contiguous()
     bw, pd = torch.empty(n, 5, 24), torch.empty(n, 5)
     x0, v = torch.empty(n, 5, 3), torch.empty(n, 5, 3)
+    idx_bf = torch.empty(n, 5, 4, dtype=torch.int32)
     emul.emul_knn_lbs(fp(pp), fp(pw), fp(ln), pp.shape[1], fp(A), fp(bA), fp(q), fp(dirs), C.c_longlong(n),
-                      fp(bw), fp(pd), fp(x0), fp(v))
+                      fp(bw), fp(pd), fp(x0), fp(v), C.c_int(0), fp(idx_bf), None)
+    # the production search (Morton clusters + AABB pruning) selects exactly the brute-force neighbours
+    bw_c, pd_c, x0_c, v_c = (torch.empty_like(t) for t in (bw, pd, x0, v))
+    idx_cl = torch.empty_like(idx_bf)
+    scanned = C.c_longlong(0)
+    emul.emul_knn_lbs(fp(pp), fp(pw), fp(ln), pp.shape[1], fp(A), fp(bA), fp(q), fp(dirs), C.c_longlong(n),
+                      fp(bw_c), fp(pd_c), fp(x0_c), fp(v_c), C.c_int(1), fp(idx_cl), C.byref(scanned))
+    assert torch.equal(idx_bf, idx_cl)
+    assert torch.equal(bw, bw_c) and torch.equal(pd, pd_c) and torch.equal(x0, x0_c)
+    total_clusters = int(sum((int(c) + 31) // 32 for c in ln)) * n
+    print(f"[knn] clusters scanned {scanned.value} of {total_clusters} ({scanned.value / total_clusters:.3f})")
+    assert scanned.value < 0.35 * total_clusters
     rbw, rpd = O.knn_blend_weights(q, pp, pw, ln)
     assert torch.allclose(bw, rbw, atol=1e-6, rtol=1e-5), (bw - rbw).abs().max()
     assert torch.allclose(pd, rpd, atol=1e-6, rtol=1e-5)
