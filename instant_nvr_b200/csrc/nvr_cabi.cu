@@ -12,6 +12,7 @@
 
 #include "../../include/nvr_b200.h"
 #include "nvr_kernels.cuh"
+#include "nvr_mlp_tc.cuh"
 
 struct NvrEngine {
     NvrConfig cfg;
@@ -29,6 +30,8 @@ struct NvrEngine {
     float* d_dist = nullptr; size_t dist_cap = 0;
     float4* d_verts = nullptr; size_t verts_cap = 0;      // clustered vertices + 2 AABB corners per cluster
     int* d_cl_off = nullptr;
+    PartMlpDev* d_part_mlp = nullptr;       // device copy of part_mlp[] for k_mlp_prep
+    float* d_mlp_blocks = nullptr;          // NVR_PARTS packed tcgen05 parameter blocks (mlp_mode 1)
     int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
     long long launches = 0;
     long long last_points = 0;
@@ -112,7 +115,10 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
         cudaMalloc(&h->d_counters_snapshot, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
         cudaMemset(h->d_counters_snapshot, 0, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_SORT_MAX * 8) != cudaSuccess) {
+        cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_SORT_MAX * 8) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaMalloc(&h->d_part_mlp, NVR_PARTS * sizeof(PartMlpDev)) != cudaSuccess ||
+        cudaMalloc(&h->d_mlp_blocks, (size_t)NVR_PARTS * TC_BLOCK_FLOATS * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
         delete h;
         return 5;
@@ -124,7 +130,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
 extern "C" int nvr_destroy(NvrHandle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_counters_snapshot);
+    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_part_mlp); cudaFree(h->d_mlp_blocks); cudaFree(h->d_counters_snapshot);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
     delete h;
@@ -171,6 +177,8 @@ extern "C" int nvr_bind_params(NvrHandle h, const NvrParams* p) {
     h->def_grid = to_dev(dg);
     h->def_mlp = DeformerMlp{p->deformer_mlp[0].weight, p->deformer_mlp[0].bias, p->deformer_mlp[1].weight,
                              p->deformer_mlp[1].bias, p->deformer_mlp[2].weight, p->deformer_mlp[2].bias};
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    NVR_CHECK(h, cudaMemcpy(h->d_part_mlp, h->part_mlp, sizeof(h->part_mlp), cudaMemcpyHostToDevice));
     h->have_params = true;
     return 0;
 }
@@ -273,6 +281,12 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     { StageTimer t(h, st, NVR_STAGE_WARP);
     k_warp<<<dim3(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS), WARP_THREADS, 0, st>>>(
         h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg); }
+    const bool tc = h->cfg.mlp_mode == 1;
+    if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
+        StageTimer t(h, st, NVR_STAGE_MLP);
+        k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
+        h->launches++;
+    }
     for (int p = 0; p < NVR_NUM_PARTS; ++p) {
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
@@ -280,8 +294,12 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
                                                          el, NVR_EMB_STRIDE); }
         StageTimer t(h, st, NVR_STAGE_MLP);
-        k_mlp<<<grid_for(n, MLP_TILE, sm), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[p], p, h->fdev.latent_index,
-                                                                      w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
+        if (tc)
+            k_mlp_tc<<<grid_for(n, 256, sm), TC_THREADS, TC_SMEM_BYTES, st>>>(h->d_mlp_blocks + (size_t)p * TC_BLOCK_FLOATS, h->part_mlp[p].n_rgb, p,
+                                                                     w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
+        else
+            k_mlp<<<grid_for(n, MLP_TILE, sm), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[p], p, h->fdev.latent_index,
+                                                                          w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
     }
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 3 + 2 * NVR_NUM_PARTS;
@@ -411,8 +429,16 @@ extern "C" int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const f
     if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_part_mlp: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
     k_make_pairs<<<(int)((n + 255) / 256), 256, 0, st>>>(dirs, (int)n, w.pairs, w.counters);
-    k_mlp<<<grid_for(n, MLP_TILE, h->sm_count), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[part], 0, h->fdev.latent_index, w.counters,
-                                                                          w.pairs, emb, (float4*)raw, 1);
+    if (h->cfg.mlp_mode == 1) {
+        if (((uintptr_t)emb & 15) != 0) return fail(h, "nvr_part_mlp: emb must be 16-byte aligned (rows of 20 floats)");
+        k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
+        k_mlp_tc<<<grid_for(n, 256, h->sm_count), TC_THREADS, TC_SMEM_BYTES, st>>>(h->d_mlp_blocks + (size_t)part * TC_BLOCK_FLOATS,
+                                                                           h->part_mlp[part].n_rgb, 0, w.counters, w.pairs, emb, (float4*)raw, 1);
+        h->launches++;
+    } else {
+        k_mlp<<<grid_for(n, MLP_TILE, h->sm_count), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[part], 0, h->fdev.latent_index, w.counters,
+                                                                              w.pairs, emb, (float4*)raw, 1);
+    }
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 2;
     return 0;

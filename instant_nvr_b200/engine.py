@@ -7,6 +7,7 @@ references so the storages outlive the binding, and re-binds when a storage poin
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -28,12 +29,18 @@ def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
     return t
 
 
+DEFAULT_MLP_MODE = 1
+
+
 class Engine:
     def __init__(self, cfg: PathConfig, device: Optional[torch.device] = None, max_points_per_pass: int = 8 << 20,
-                 mlp_mode: int = 0):
+                 mlp_mode: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("instant_nvr_b200 needs a CUDA device: the hot path has no CPU implementation")
         cfg.check_supported()
+        if mlp_mode is None:        # 1: tcgen05 3xTF32 tensor-core tiles (default); 0: fp32 FFMA tiles
+            mlp_mode = int(os.environ.get("NVR_MLP_MODE", DEFAULT_MLP_MODE))
+        self.mlp_mode = int(mlp_mode)
         self.cfg = cfg
         self.lib = cabi.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")

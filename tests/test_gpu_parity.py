@@ -128,6 +128,34 @@ def test_part_mlp(gpu):
         assert err < 5e-6, (pid, err)
 
 
+def test_part_mlp_tensor_core(gpu):
+    """The tcgen05 3xTF32 MLP kernel against the fp32 oracle (and against our fp32 FFMA kernel)."""
+    from instant_nvr_b200.engine import Engine
+    g = torch.Generator().manual_seed(14)
+    net, sd, frame = gpu["nets"][200.0], gpu["sds"][200.0], gpu["frame"]
+    eng_tc = Engine(gpu["cfg"], mlp_mode=1)
+    eng_tc.bind_params(net)
+    eng_ff = Engine(gpu["cfg"], mlp_mode=0)
+    eng_ff.bind_params(net)
+    lat = int(frame["latent_index"][0])
+    for pid in range(5):
+        for n in (1, 127, 128, 129, 20000 + 37 * pid):
+            e = torch.cat([torch.rand(n, 3, generator=g), torch.randn(n, 16, generator=g)], -1)
+            v = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+            ours = eng_tc.part_mlp(pid, e.cuda(), v.cuda(), gpu["gbatch"]).cpu()
+            ffma = eng_ff.part_mlp(pid, e.cuda(), v.cuda(), gpu["gbatch"]).cpu()
+            pre = f"tpose_human.part_networks.{pid}."
+            h = O.mlp_softplus(e, sd, pre + "occ.linears.")
+            occ = 1 - torch.exp(-torch.nn.functional.softplus(h[..., :1]))
+            inp = torch.cat([e, O.posenc(v), h[..., 1:], sd[pre + "rgb_latent"][lat][None].expand(n, -1)], -1)
+            rgb = O.mlp_softplus(inp, sd, pre + "rgb.linears.").sigmoid()
+            ref = torch.cat([rgb, occ], -1)
+            err = (ours - ref).abs().max().item()
+            err_ff = (ours - ffma).abs().max().item()
+            diag("part_mlp_tc", part=pid, n=n, max_err_vs_oracle=err, max_err_vs_ffma=err_ff)
+            assert err < 2e-5, (pid, n, err)          # north-star bound is 1e-4; the fp32 FFMA kernel holds 5e-6
+
+
 def _points(gpu, n_rays_side=24, S=24):
     from instant_nvr_b200.synthetic import make_rays
     rays = make_rays(gpu["frame"], n_rays_side, n_rays_side)
