@@ -227,12 +227,14 @@ def main():
     frame_h = torch.empty(n_total, 4).pin_memory() if world > 1 else None
 
     def step_device():
+        eng.bind_frame(gframe, force=True)      # every step is a new frame: per-frame preparation is inside the timed region
         rgb, acc = eng.render_rays(dev["ray_o"], dev["ray_d"], dev["near"], dev["far"], N_SAMPLES)
         if world > 1:
             return assemble(torch.cat([rgb, acc[:, None]], 1), n_total, rank, world)
         return rgb
 
     def step_e2e():
+        eng.bind_frame(gframe, force=True)
         if world == 1:
             eng.render_rays_host(host["ray_o"], host["ray_d"], host["near"], host["far"], N_SAMPLES, rgb_h, acc_h)
         else:

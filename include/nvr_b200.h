@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 2
+#define NVR_ABI_VERSION 3
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -101,6 +101,12 @@ typedef struct NvrFrame {
     const float* tbounds;          /* (2,3) */
     const float* frame_dim;        /* (1) f32 */
     const int64_t* latent_index;   /* (1) int64 */
+    int64_t topology_key;          /* 0: rebuild the KNN vertex partition for this frame.  Non-zero: the caller
+                                      vouches that frames with equal keys list the same vertices in the same
+                                      order in part_pts (same subject, same part split), so the partition of the
+                                      previous frame is reused and only vertex positions / boxes are refreshed.
+                                      The search is exact for ANY partition; the key only trades build time
+                                      against box tightness. */
 } NvrFrame;
 
 typedef struct NvrConfig {

@@ -12,7 +12,7 @@ from typing import Optional
 
 MAX_LEVELS = 16
 NUM_PARTS = 5
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnvr_b200.so")
@@ -53,7 +53,7 @@ class NvrFrame(C.Structure):
         ("maxlen", C.c_int32), ("_pad0", C.c_int32),
         ("A", C.c_void_p), ("big_A", C.c_void_p),
         ("tuv", C.c_void_p), ("tuv_dims", C.c_int32 * 3), ("_pad1", C.c_int32), ("tbounds", C.c_void_p),
-        ("frame_dim", C.c_void_p), ("latent_index", C.c_void_p),
+        ("frame_dim", C.c_void_p), ("latent_index", C.c_void_p), ("topology_key", C.c_int64),
     ]
 
 

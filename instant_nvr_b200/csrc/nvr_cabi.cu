@@ -30,6 +30,8 @@ struct NvrEngine {
     float* d_dist = nullptr; size_t dist_cap = 0;
     float4* d_verts = nullptr; size_t verts_cap = 0;      // clustered vertices + 2 AABB corners per cluster
     int* d_cl_off = nullptr;
+    int* d_perm = nullptr; size_t perm_cap = 0;            // KD partition: cluster slot -> vertex index in its part
+    long long perm_key = 0; int perm_maxlen = 0;           // topology the partition was built for
     PartMlpDev* d_part_mlp = nullptr;       // device copy of part_mlp[] for k_mlp_prep
     float* d_mlp_blocks = nullptr;          // NVR_PARTS packed tcgen05 parameter blocks (mlp_mode 1)
     int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
@@ -115,7 +117,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
         cudaMalloc(&h->d_counters_snapshot, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
         cudaMemset(h->d_counters_snapshot, 0, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_SORT_MAX * 8) != cudaSuccess ||
+        cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_CLUSTER_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
         cudaMalloc(&h->d_part_mlp, NVR_PARTS * sizeof(PartMlpDev)) != cudaSuccess ||
         cudaMalloc(&h->d_mlp_blocks, (size_t)NVR_PARTS * TC_BLOCK_FLOATS * sizeof(float)) != cudaSuccess) {
@@ -130,7 +132,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
 extern "C" int nvr_destroy(NvrHandle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_part_mlp); cudaFree(h->d_mlp_blocks); cudaFree(h->d_counters_snapshot);
+    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_perm); cudaFree(h->d_part_mlp); cudaFree(h->d_mlp_blocks); cudaFree(h->d_counters_snapshot);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
     delete h;
@@ -209,13 +211,25 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
         NVR_CHECK(h, cudaMalloc(&h->d_verts, n_verts * sizeof(float4)));
         h->verts_cap = n_verts;
     }
+    if (max_cl * NVR_CL > h->perm_cap) {
+        NVR_CHECK(h, cudaFree(h->d_perm));
+        h->d_perm = nullptr; h->perm_cap = 0; h->perm_key = 0;
+        NVR_CHECK(h, cudaMalloc(&h->d_perm, max_cl * NVR_CL * sizeof(int)));
+        h->perm_cap = max_cl * NVR_CL;
+    }
     StageTimer tm_(h, stream, NVR_STAGE_PREP);
     k_frame_prep<<<std::min<int>(h->sm_count * 4, (int)((n_vox + 255) / 256)), 256, 0, stream>>>(
         f->pbw, (int)n_vox, f->pbw_channels, h->d_dist);
     float4* cl_lo = h->d_verts + max_cl * NVR_CL;
     float4* cl_hi = cl_lo + max_cl;
-    k_cluster_verts<<<NVR_NUM_PARTS, 1024, NVR_SORT_MAX * 8, stream>>>(f->part_pts, (const long long*)f->lengths2, f->maxlen,
-                                                                      h->d_verts, cl_lo, cl_hi, h->d_cl_off);
+    if (f->topology_key == 0 || f->topology_key != h->perm_key || f->maxlen != h->perm_maxlen) {
+        k_cluster_verts<<<NVR_NUM_PARTS, 1024, NVR_CLUSTER_SMEM, stream>>>(f->part_pts, (const long long*)f->lengths2, f->maxlen,
+                                                                          h->d_perm, h->d_cl_off);
+        h->perm_key = f->topology_key; h->perm_maxlen = f->maxlen;
+        h->launches++;
+    }
+    k_cluster_apply<<<std::max<int>(1, (int)((max_cl * NVR_CL + 127) / 128)), 128, 0, stream>>>(f->part_pts, f->maxlen, h->d_perm, h->d_cl_off,
+                                                                                             h->d_verts, cl_lo, cl_hi);
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 2;
     h->frame = *f;
@@ -291,7 +305,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
         { StageTimer t(h, st, NVR_STAGE_EMBED);
-        k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
+        k_embed<<<grid_for(n, 256, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
                                                          el, NVR_EMB_STRIDE); }
         StageTimer t(h, st, NVR_STAGE_MLP);
         if (tc)
@@ -413,7 +427,7 @@ extern "C" int nvr_embed_part(NvrHandle h, int32_t part, const float* xyz, int64
     if (n == 0) return 0;
     if (n >= (1ll << 31)) return fail(h, "nvr_embed_part: n must be < 2^31");
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
-    k_embed<<<grid_for(n, 128, h->sm_count * 2), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
+    k_embed<<<grid_for(n, 256, h->sm_count * 2), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return 0;

@@ -2,7 +2,8 @@
 //
 //   k_frame_prep   per frame: distance channel of pbw -> compact volume, part vertices -> packed float4
 //   k_cull         sample gen (ray mode) / point fetch, world->pose, distance cull, block compaction
-//   k_cluster_verts per frame: Morton-sorted vertex clusters + AABBs (the KNN acceleration structure)
+//   k_cluster_verts per frame: balanced KD partition of each part's vertices into clusters + AABBs
+//                  (the KNN acceleration structure)
 //   k_knn          per survivor: 5x exact K=4 NN (group search over the clusters), Gaussian weights,
 //                  per-part append of flagged (sample, part) neighbour records
 //   k_warp         per flagged pair: blend weights, LBS to big pose, deformer -> canonical point + dir
@@ -63,20 +64,31 @@ __global__ void k_frame_prep(const float* __restrict__ pbw, int n_vox, int C, fl
     for (int i = tid; i < n_vox; i += nth) dist[i] = pbw[(long long)i * C + (C - 1)];
 }
 
-// Per-frame KNN acceleration structure, one CTA per part: sort the part's posed vertices along a
-// 30-bit Morton curve over the part's bounding box (bitonic sort of (code << 32 | index) keys in
-// shared memory), cut the sorted run into clusters of NVR_CL vertices and record each cluster's
-// AABB.  The search in k_warp stays EXACT: clusters are only skipped when their AABB lower bound
-// exceeds the current 4th-best distance.  Padding vertices are +inf (never selected).
+// Per-frame KNN acceleration structure, one CTA per part: a balanced KD partition of the part's posed
+// vertices into clusters of NVR_CL (median splits along the longest axis of each segment's bounding
+// box, left half rounded to whole clusters), plus each cluster's AABB.  Every level is ONE bitonic
+// sort in shared memory of 64-bit keys (segment | order-preserving coordinate bits | vertex index),
+// so segments are sorted side by side; ~log2(#clusters) levels, tens of microseconds per frame.
+// (Tighter boxes than a Morton curve: ~1.7x fewer clusters survive the lower-bound test.)
+// The search in k_knn stays EXACT whatever the partition: clusters are only skipped when their AABB
+// lower bound exceeds the current 4th-best distance.  Padding vertices are +inf (never selected).
 #define NVR_SORT_MAX 8192
+#define NVR_CL_MAX (NVR_SORT_MAX / NVR_CL)
+#define NVR_CLUSTER_SMEM (NVR_SORT_MAX * 8 + NVR_CL_MAX * (2 * 2 + 6 * 4))
+
+__device__ __forceinline__ unsigned int float_order_bits(float f) {   // monotone float -> uint
+    const unsigned int u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
 __global__ void __launch_bounds__(1024)
 k_cluster_verts(const float* __restrict__ part_pts, const long long* __restrict__ lengths2, int maxlen,
-                float4* __restrict__ verts, float4* __restrict__ cl_lo, float4* __restrict__ cl_hi,
-                int* __restrict__ cl_off) {
-    extern __shared__ unsigned long long s_key[];
-    __shared__ float s_red[6][32];
-    __shared__ float s_box[6];
-    const int part = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+                int* __restrict__ perm, int* __restrict__ cl_off) {
+    extern __shared__ unsigned long long s_key[];                  // [NVR_SORT_MAX]
+    unsigned short* s_ra = reinterpret_cast<unsigned short*>(s_key + NVR_SORT_MAX);   // segment [ra, rb) of each cluster
+    unsigned short* s_rb = s_ra + NVR_CL_MAX;
+    unsigned int* s_box = reinterpret_cast<unsigned int*>(s_rb + NVR_CL_MAX);         // [6][NVR_CL_MAX] order bits, by segment start
+    const int part = blockIdx.x, tid = threadIdx.x;
     int coff = 0, n = 0;
     for (int p = 0; p < NVR_PARTS; ++p) {
         long long len = lengths2[p];
@@ -84,84 +96,121 @@ k_cluster_verts(const float* __restrict__ part_pts, const long long* __restrict_
         if (p == part) n = (int)len;
         if (p < part) coff += (int)((len + NVR_CL - 1) / NVR_CL);
     }
-    if (tid == 0) cl_off[part + 1] = coff + (n + NVR_CL - 1) / NVR_CL;
+    const int ncl = (n + NVR_CL - 1) / NVR_CL;
+    if (tid == 0) cl_off[part + 1] = coff + ncl;
     if (part == 0 && tid == 0) cl_off[0] = 0;
     const float* src = part_pts + (long long)part * maxlen * 3;
-    // bounding box of the part
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int j = tid; j < n; j += blockDim.x)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { const float v = src[j * 3 + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
-        }
-        if (lane == 0) { s_red[a][wid] = lo[a]; s_red[3 + a][wid] = hi[a]; }
-    }
-    __syncthreads();
-    if (tid < 6) {
-        float r = s_red[tid][0];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = tid < 3 ? fminf(r, s_red[tid][w]) : fmaxf(r, s_red[tid][w]);
-        s_box[tid] = r;
-    }
-    __syncthreads();
     int M = 32;
     while (M < n) M <<= 1;
-    for (int j = tid; j < M; j += blockDim.x) {
-        unsigned long long key = ~0ull;
-        if (j < n) {
-            unsigned code = 0;
+    for (int j = tid; j < M; j += blockDim.x) s_key[j] = j < n ? (unsigned long long)j : ~0ull;
+    for (int c = tid; c < ncl; c += blockDim.x) { s_ra[c] = 0; s_rb[c] = (unsigned short)ncl; }
+    __syncthreads();
+    int span = ncl;                                                // largest segment, in clusters
+    while (span > 1) {
+        // 1. bounding box of every segment (keyed by its first cluster)
+        for (int c = tid; c < ncl; c += blockDim.x)
+            if (s_ra[c] == c)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { s_box[a * NVR_CL_MAX + c] = 0xffffffffu; s_box[(3 + a) * NVR_CL_MAX + c] = 0u; }
+        __syncthreads();
+        for (int i0 = tid - (tid & 31); i0 < n; i0 += blockDim.x) {   // warp-uniform trip count
+            const int i = i0 + (tid & 31);
+            const bool valid = i < n;
+            const int j = valid ? (int)(s_key[i] & 0x1fffull) : 0, seg = valid ? (int)s_ra[i / NVR_CL] : -1;
+            const bool whole_warp = __match_any_sync(0xffffffffu, seg) == 0xffffffffu;   // one segment, all valid
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const float ext = s_box[3 + a] - s_box[a];
-                float t = ext > 0.0f ? (src[j * 3 + a] - s_box[a]) / ext : 0.0f;
-                int q = (int)(t * 1024.0f);
-                q = q < 0 ? 0 : (q > 1023 ? 1023 : q);            // NaN coordinates land in cell 0
-                unsigned x = (unsigned)q;                         // spread 10 bits to every third position
-                x = (x | (x << 16)) & 0x030000FFu;
-                x = (x | (x << 8)) & 0x0300F00Fu;
-                x = (x | (x << 4)) & 0x030C30C3u;
-                x = (x | (x << 2)) & 0x09249249u;
-                code |= x << a;
-            }
-            key = ((unsigned long long)code << 32) | (unsigned)j;
-        }
-        s_key[j] = key;
-    }
-    __syncthreads();
-    for (int k = 2; k <= M; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < M; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = s_key[i], b = s_key[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { s_key[i] = b; s_key[ixj] = a; }
+                const unsigned int u = float_order_bits(src[j * 3 + a]);
+                if (whole_warp) {
+                    const unsigned int lo = __reduce_min_sync(0xffffffffu, u), hi = __reduce_max_sync(0xffffffffu, u);
+                    if ((tid & 31) == 0) { atomicMin(&s_box[a * NVR_CL_MAX + seg], lo); atomicMax(&s_box[(3 + a) * NVR_CL_MAX + seg], hi); }
+                } else if (valid) {
+                    atomicMin(&s_box[a * NVR_CL_MAX + seg], u);
+                    atomicMax(&s_box[(3 + a) * NVR_CL_MAX + seg], u);
                 }
             }
-            __syncthreads();
         }
-    const int ncl = (n + NVR_CL - 1) / NVR_CL;
-    for (int i = tid; i < ncl * NVR_CL; i += blockDim.x) {
-        float4 v = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(0));
-        if (i < n) {
-            const int j = (int)(s_key[i] & 0xffffffffull);
-            v = make_float4(src[j * 3], src[j * 3 + 1], src[j * 3 + 2], __int_as_float(j));
-        }
-        verts[(long long)coff * NVR_CL + i] = v;
-    }
-    for (int c = tid; c < ncl; c += blockDim.x) {
-        float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int i = c * NVR_CL; i < min(n, (c + 1) * NVR_CL); ++i) {
-            const int j = (int)(s_key[i] & 0xffffffffull);
+        __syncthreads();
+        // 2. keys: segment | coordinate along the segment's longest axis | vertex
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int j = (int)(s_key[i] & 0x1fffull), seg = s_ra[i / NVR_CL];
+            int ax = 0;
+            float best = -1.0f;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { const float v = src[j * 3 + a]; bl[a] = fminf(bl[a], v); bh[a] = fmaxf(bh[a], v); }
+            for (int a = 0; a < 3; ++a) {
+                // order bits back to floats: extent = hi - lo
+                unsigned int ul = s_box[a * NVR_CL_MAX + seg], uh = s_box[(3 + a) * NVR_CL_MAX + seg];
+                ul ^= (ul >> 31) ? 0x80000000u : 0xffffffffu;
+                uh ^= (uh >> 31) ? 0x80000000u : 0xffffffffu;
+                const float e = __uint_as_float(uh) - __uint_as_float(ul);
+                if (e > best) { best = e; ax = a; }
+            }
+            s_key[i] = ((unsigned long long)seg << 45) | ((unsigned long long)float_order_bits(src[j * 3 + ax]) << 13) | (unsigned)j;
         }
-        cl_lo[coff + c] = make_float4(bl[0], bl[1], bl[2], __int_as_float(min(n, (c + 1) * NVR_CL) - c * NVR_CL));
-        cl_hi[coff + c] = make_float4(bh[0], bh[1], bh[2], 0.f);
+        __syncthreads();
+        // 3. one bitonic sort orders every segment along its own axis
+        for (int k = 2; k <= M; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int i = tid; i < M; i += blockDim.x) {
+                    const int ixj = i ^ jj;
+                    if (ixj > i) {
+                        const unsigned long long x = s_key[i], y = s_key[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { s_key[i] = y; s_key[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        // 4. split every segment of more than one cluster at its middle cluster
+        for (int c = tid; c < ncl; c += blockDim.x) {
+            const int ra = s_ra[c], rb = s_rb[c];
+            if (rb - ra > 1) {
+                const int mid = ra + (rb - ra) / 2;
+                if (c < mid) s_rb[c] = (unsigned short)mid; else s_ra[c] = (unsigned short)mid;
+            }
+        }
+        span = (span + 1) / 2;
+        __syncthreads();
+    }
+    // the partition: slot -> vertex index within the part (-1 = padding); positions are filled by k_cluster_apply
+    for (int i = tid; i < ncl * NVR_CL; i += blockDim.x) perm[(long long)coff * NVR_CL + i] = i < n ? (int)(s_key[i] & 0x1fffull) : -1;
+}
+
+// Every frame: gather the posed vertices into cluster order and recompute the cluster AABBs.
+// 16 lanes per cluster (NVR_CL == 16): lane = slot, min/max by shuffles inside the half-warp.
+__global__ void __launch_bounds__(128)
+k_cluster_apply(const float* __restrict__ part_pts, int maxlen, const int* __restrict__ perm, const int* __restrict__ cl_off,
+                float4* __restrict__ verts, float4* __restrict__ cl_lo, float4* __restrict__ cl_hi) {
+    static_assert(NVR_CL == 16, "k_cluster_apply maps one half-warp to one cluster");
+    const int total = cl_off[NVR_PARTS];
+    const int lane16 = threadIdx.x & 15;
+    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; c < ((total + 1) & ~1); c += (gridDim.x * blockDim.x) >> 4) {
+        const bool in = c < total;                                 // clusters are handled in warp-wide pairs
+        int part = 0;
+#pragma unroll
+        for (int p = 1; p < NVR_PARTS; ++p) part += (in && c >= cl_off[p]) ? 1 : 0;
+        const int j = in ? perm[(long long)c * NVR_CL + lane16] : -1;
+        float x = INFINITY, y = INFINITY, z = INFINITY;
+        if (j >= 0) {
+            const float* s = part_pts + ((long long)part * maxlen + j) * 3;
+            x = s[0]; y = s[1]; z = s[2];
+        }
+        if (in) verts[(long long)c * NVR_CL + lane16] = make_float4(x, y, z, __int_as_float(j >= 0 ? j : 0));
+        float lo[3] = {x, y, z}, hi[3] = {j >= 0 ? x : -INFINITY, j >= 0 ? y : -INFINITY, j >= 0 ? z : -INFINITY};
+        int cnt = j >= 0 ? 1 : 0;
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+            }
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        }
+        if (in && lane16 == 0) {
+            cl_lo[c] = make_float4(lo[0], lo[1], lo[2], __int_as_float(cnt));
+            cl_hi[c] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        }
     }
 }
 
@@ -209,21 +258,25 @@ __device__ __forceinline__ void knn_part_group(const FrameDev& fr, int part, con
         if (ob < best || (ob == best && os < seed)) { best = ob; seed = os; }
     }
     U *= 1.00001f;
-    // round -1 holds only the seed (every live lane scans it: k.d2[3] is still +inf); rounds 0.. hold the rest
+    // round -1 holds only the seed (every live lane scans it: its 4th-best is still +inf); rounds 0.. hold the rest
     for (int cb = -32; cb < ncl; cb += 32) {
         const int c = cb + lane;
         bool cand = lane == 0;
         if (cb >= 0) {
+            // group bound, refreshed every round: no lane needs a cluster whose box-to-box gap exceeds the
+            // LARGEST current 4th-best distance of the warp (non-negative floats order like their bits)
+            const float worst = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? (unsigned int)(k.key[3] >> 32) : 0u));
+            const float bound = fminf(U, worst * 1.00001f);
             cand = false;
             if (c < ncl && c != seed)
-                cand = !(box_gap2(__ldg(fr.cl_lo + c0 + c), __ldg(fr.cl_hi + c0 + c), qlo, qhi) * NVR_PRUNE_SLACK > U);
+                cand = !(box_gap2(__ldg(fr.cl_lo + c0 + c), __ldg(fr.cl_hi + c0 + c), qlo, qhi) * NVR_PRUNE_SLACK > bound);
         }
         unsigned m = __ballot_sync(0xffffffffu, cand);
         while (m) {
             const int cc = cb < 0 ? seed : cb + __ffs(m) - 1;
             m &= m - 1;
             const float lb = nvr_aabb_lb(__ldg(fr.cl_lo + c0 + cc), __ldg(fr.cl_hi + c0 + cc), p);
-            const bool need = live && !(lb * NVR_PRUNE_SLACK > k.d2[3]);
+            const bool need = live && !(lb * NVR_PRUNE_SLACK > nvr_knn_d2(k, 3));
             if (__any_sync(0xffffffffu, need)) nvr_knn_scan(fr.verts + (long long)(c0 + cc) * NVR_CL, NVR_CL, p, k);
         }
     }
@@ -344,7 +397,7 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, const float4* __res
                 wbase = __shfl_sync(0xffffffffu, wbase, 0);
                 if (flag) {
 #pragma unroll
-                    for (int i = 0; i < NVR_KNN; ++i) rec.idx[i] = k.idx[i];
+                    for (int i = 0; i < NVR_KNN; ++i) rec.idx[i] = nvr_knn_idx(k, i);
                     rec.surv = s; rec._pad[0] = rec._pad[1] = rec._pad[2] = 0;
                     recs[(long long)part * cap + wbase + __popc(ballot & ((1u << lane) - 1u))] = rec;
                 }
@@ -426,12 +479,14 @@ k_deformer(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ 
 }
 
 // -----------------------------------------------------------------------------------------
-// THE gather: part grid embedding, one 32-byte sector per lane
+// THE gather: part grid embedding, one 64-byte row = two 256-bit loads per lane
 // -----------------------------------------------------------------------------------------
-// A warp works on 16 points at a time: lane = 2*point + half.  A grid entry is one 64-byte row of 16
-// fp32 features = two 32-byte sectors; each lane fetches ONE whole sector with a single 256-bit load
-// (LDG.E.256), so every byte of every sector that moves is used and the per-point index arithmetic is
-// shared by only two lanes.  The 8 corner loads of a level are independent and issued back to back.
+// One lane = one point (32 points per warp): a grid entry is one 64-byte row of 16 fp32 features = two
+// 32-byte sectors, fetched with two 256-bit loads (LDG.E.256), so every byte of every sector that moves
+// is used and the per-point index arithmetic is paid once per point.  The 8 corners of a level go in
+// two batches of four (8 independent 32-byte loads in flight per lane).  Per corner the 16 features are
+// tree-summed and scaled by the trilinear weight (sum_c w_c sum_f t[c][f], the reference's
+// sum_f sum_c w_c t[c][f] re-associated).
 // The level loop is deliberately NOT unrolled: unrolled, the kernel is ~10k instructions and spends
 // most of its time waiting for instruction fetch (profiles/r1a: 62 % stall_no_inst); rolled it is a
 // few hundred instructions that stay in the instruction cache.
@@ -460,19 +515,15 @@ __global__ void __launch_bounds__(256, 2)
 k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
         float* __restrict__ eb, int emb_stride) {
     const int n = count_dev ? *count_dev : n_imm;
-    const int lane = threadIdx.x & 31, half = lane & 1;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool fast_mod = g.T_magic40 != 0;
     const unsigned int T32 = (unsigned int)g.T;
-    for (int base = warp * 16; base < n; base += n_warps * 16) {
-        const int pt = base + (lane >> 1);
-        const bool live = pt < n;
-        const float* xp = xb + (long long)(live ? pt : n - 1) * xstride;
+    for (int pt = blockIdx.x * blockDim.x + threadIdx.x; pt < n; pt += gridDim.x * blockDim.x) {
+        const float* xp = xb + (long long)pt * xstride;
         const float x[3] = {xp[0], xp[1], xp[2]};
         float u[3];
         nvr_normalise(g, x, u);
         float* o = eb + (long long)pt * emb_stride;
-        if (live && half == 0) { o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; }
+        o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
 #pragma unroll 1
         for (int l = 0; l < g.n_levels; ++l) {
             const int res = g.res[l];
@@ -504,22 +555,28 @@ k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restr
                     row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
                 }
             }
-            Sector v[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = ld_sector(tab + (unsigned long long)row[c] * 16 + half * 8);
             const float wx[2] = {1.0f - of[0], of[0]}, wy[2] = {1.0f - of[1], of[1]}, wz[2] = {1.0f - of[2], of[2]};
-            float acc[8];
+            float lev = 0.0f;
 #pragma unroll
-            for (int f = 0; f < 8; ++f) acc[f] = 0.0f;
+            for (int cb = 0; cb < 8; cb += 4) {
+                Sector v[4][2];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float w = (wx[(c >> 2) & 1] * wy[(c >> 1) & 1]) * wz[c & 1];      // :158-159
+                for (int c = 0; c < 4; ++c) {
+                    const float* r = tab + (unsigned long long)row[cb + c] * 16;
+                    v[c][0] = ld_sector(r);
+                    v[c][1] = ld_sector(r + 8);
+                }
 #pragma unroll
-                for (int f = 0; f < 8; ++f) acc[f] += w * v[c].v[f];                    // :160
+                for (int c = 0; c < 4; ++c) {
+                    const float* a = v[c][0].v;
+                    const float* b = v[c][1].v;
+                    const float sf = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) +
+                                     (((b[0] + b[1]) + (b[2] + b[3])) + ((b[4] + b[5]) + (b[6] + b[7])));   // :165
+                    const int cc = cb + c;
+                    lev += ((wx[(cc >> 2) & 1] * wy[(cc >> 1) & 1]) * wz[cc & 1]) * sf;                      // :158-160
+                }
             }
-            float sfeat = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-            sfeat += __shfl_xor_sync(0xffffffffu, sfeat, 1);                            // :165 sum over the 16 features
-            if (live && half == (l & 1)) o[3 + l] = sfeat;
+            o[3 + l] = lev;
         }
     }
 }
@@ -590,7 +647,7 @@ __device__ __forceinline__ void stage_bias(float* dst, int np, const LinearDev& 
 __global__ void __launch_bounds__(256)
 k_mlp(PartMlpDev pm, int part, const long long* __restrict__ latent_index, const int* __restrict__ count_dev,
       const PairRec* __restrict__ pl, const float* __restrict__ el, float4* __restrict__ raws, int out_stride) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     float* sA = sm + MLP_S_A; float* sH = sm + MLP_S_H;
     float* sB = sm + MLP_S_B;
     float* b_occ0 = sB; float* b_occ1 = sB + 64; float* b_rgb0 = sB + 84; float* b_rgb1 = sB + 148; float* b_rgbL = sB + 212;

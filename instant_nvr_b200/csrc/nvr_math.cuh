@@ -211,32 +211,47 @@ NVR_HD void nvr_sample_volume(const VolumeDev& v, const float p[3], int ch0, int
 // ---------------------------------------------------------------------------------------
 // K=4 nearest vertices -> Gaussian blend weights                 blend_utils.py:732-763
 // ---------------------------------------------------------------------------------------
+// The running 4 best neighbours, ascending.  A candidate is the 64-bit key (bits(d2) << 32 | vertex
+// index): squared distances are non-negative floats, whose bit patterns order like their values, so
+// one unsigned compare orders candidates by (d2, vertex index).  The result therefore does not depend
+// on the order in which vertices are visited and equals a stable top-k over the original vertex order
+// (ties keep the lower index) -- which is what lets the production scan walk spatial clusters.
+// NaN distances (bits above +inf) never enter.
 struct Knn4 {
-    float d2[NVR_KNN];      // ascending
-    int idx[NVR_KNN];
+    unsigned long long key[NVR_KNN];
 };
+NVR_HD unsigned int nvr_f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    unsigned int u; memcpy(&u, &f, 4); return u;
+#endif
+}
+NVR_HD float nvr_u2f(unsigned int u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+NVR_HD float nvr_knn_d2(const Knn4& k, int i) { return nvr_u2f((unsigned int)(k.key[i] >> 32)); }
+NVR_HD int nvr_knn_idx(const Knn4& k, int i) { return (int)(unsigned int)k.key[i]; }
 NVR_HD void nvr_knn_init(Knn4& k) {
 #pragma unroll
-    for (int i = 0; i < NVR_KNN; ++i) { k.d2[i] = INFINITY; k.idx[i] = 0; }
+    for (int i = 0; i < NVR_KNN; ++i) k.key[i] = 0x7f800000ull << 32;          // (+inf, vertex 0)
 }
-// Candidates are ordered by (d2, vertex index): the result does not depend on the order in which
-// vertices are visited, and equals a stable top-k over the original vertex order (ties keep the
-// lower index).  That freedom is what lets the production scan walk spatially sorted clusters.
-NVR_HD bool nvr_knn_less(float d2a, int ja, float d2b, int jb) { return d2a < d2b || (d2a == d2b && ja < jb); }
+// branch-free sorted insertion: bubble the candidate through the 4 slots
 NVR_HD void nvr_knn_insert(Knn4& k, float d2, int j) {
-    if (nvr_knn_less(d2, j, k.d2[3], k.idx[3])) {
-        if (nvr_knn_less(d2, j, k.d2[2], k.idx[2])) {
-            k.d2[3] = k.d2[2]; k.idx[3] = k.idx[2];
-            if (nvr_knn_less(d2, j, k.d2[1], k.idx[1])) {
-                k.d2[2] = k.d2[1]; k.idx[2] = k.idx[1];
-                if (nvr_knn_less(d2, j, k.d2[0], k.idx[0])) {
-                    k.d2[1] = k.d2[0]; k.idx[1] = k.idx[0];
-                    k.d2[0] = d2; k.idx[0] = j;
-                } else { k.d2[1] = d2; k.idx[1] = j; }
-            } else { k.d2[2] = d2; k.idx[2] = j; }
-        } else { k.d2[3] = d2; k.idx[3] = j; }
+    unsigned long long nk = ((unsigned long long)nvr_f2u(d2) << 32) | (unsigned int)j;
+#pragma unroll
+    for (int i = 0; i < NVR_KNN; ++i) {
+        const unsigned long long lo = k.key[i] < nk ? k.key[i] : nk, hi = k.key[i] < nk ? nk : k.key[i];
+        k.key[i] = lo;
+        nk = hi;
     }
 }
+// could (d2, any index) still enter?  (d2 <= current 4th-best distance; false for NaN)
+NVR_HD bool nvr_knn_admits(const Knn4& k, float d2) { return nvr_f2u(d2) <= (unsigned int)(k.key[NVR_KNN - 1] >> 32); }
 
 NVR_HD float nvr_dist2(const float p[3], const float4& v) {
     const float dx = p[0] - v.x, dy = p[1] - v.y, dz = p[2] - v.z;
@@ -259,29 +274,27 @@ NVR_HD int nvr_vert_id(const float4& v) {
 }
 
 // verts: (x, y, z, bit pattern of the ORIGINAL vertex index) of one run of vertices.  Exact.
-// Vertices are taken four at a time: the common case (none of the four beats the current 4th-best)
-// costs the distance arithmetic plus one compare and one branch.
+// Vertices are taken four at a time: when none of the four can enter, a group costs the distance
+// arithmetic plus one compare and one branch.
 NVR_HD void nvr_knn_scan(const float4* verts, int count, const float p[3], Knn4& k) {
     int j = 0;
 #pragma unroll 2
     for (; j + 4 <= count; j += 4) {
-        const float da = nvr_dist2(p, nvr_ld_vert(verts + j)), db = nvr_dist2(p, nvr_ld_vert(verts + j + 1)),
-                    dc = nvr_dist2(p, nvr_ld_vert(verts + j + 2)), dd = nvr_dist2(p, nvr_ld_vert(verts + j + 3));
-        if (fminf(fminf(da, db), fminf(dc, dd)) <= k.d2[3]) {
-            // rare path, kept rolled (one insertion site): re-read the four vertices one by one
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                const float4 v = nvr_ld_vert(verts + j + q);
-                const float d2 = nvr_dist2(p, v);
-                if (d2 <= k.d2[3]) nvr_knn_insert(k, d2, nvr_vert_id(v));
-            }
+        const float4 a = nvr_ld_vert(verts + j), b = nvr_ld_vert(verts + j + 1), c = nvr_ld_vert(verts + j + 2),
+                     d = nvr_ld_vert(verts + j + 3);
+        const float da = nvr_dist2(p, a), db = nvr_dist2(p, b), dc = nvr_dist2(p, c), dd = nvr_dist2(p, d);
+        if (nvr_knn_admits(k, fminf(fminf(da, db), fminf(dc, dd)))) {
+            if (nvr_knn_admits(k, da)) nvr_knn_insert(k, da, nvr_vert_id(a));
+            if (nvr_knn_admits(k, db)) nvr_knn_insert(k, db, nvr_vert_id(b));
+            if (nvr_knn_admits(k, dc)) nvr_knn_insert(k, dc, nvr_vert_id(c));
+            if (nvr_knn_admits(k, dd)) nvr_knn_insert(k, dd, nvr_vert_id(d));
         }
     }
 #pragma unroll 1
     for (; j < count; ++j) {
         const float4 v = nvr_ld_vert(verts + j);
         const float d2 = nvr_dist2(p, v);
-        if (d2 <= k.d2[3]) nvr_knn_insert(k, d2, nvr_vert_id(v));
+        if (nvr_knn_admits(k, d2)) nvr_knn_insert(k, d2, nvr_vert_id(v));
     }
 }
 
@@ -298,7 +311,7 @@ NVR_HD float nvr_aabb_lb(const float4& lo, const float4& hi, const float p[3]) {
 #ifdef NVR_CL_OVERRIDE
 #define NVR_CL NVR_CL_OVERRIDE
 #else
-#define NVR_CL 32
+#define NVR_CL 16
 #endif
 // vertices per spatial cluster (one AABB each)
 #define NVR_PRUNE_SLACK 0.999999f
@@ -309,7 +322,7 @@ NVR_HD float nvr_knn_weights(const Knn4& k, float w[NVR_KNN]) {
     float d[NVR_KNN], wsum = 0.0f;
 #pragma unroll
     for (int i = 0; i < NVR_KNN; ++i) {
-        d[i] = sqrtf(k.d2[i]);                                   // cast_knn_points :736
+        d[i] = sqrtf(nvr_knn_d2(k, i));                          // cast_knn_points :736
         w[i] = expf(-(d[i] * d[i]) / 0.01125f);                  // :746, 2*radius^2 = 2*0.075^2
         wsum += w[i];
     }
@@ -334,8 +347,10 @@ NVR_HD float nvr_blend_joint(const int idx[NVR_KNN], const float w[NVR_KNN], con
 // (bw[24], pdist) in one call -- host emulation and per-stage tests.
 NVR_HD float nvr_knn_blend(const Knn4& k, const float* pbw_part, float bw[NVR_JOINTS]) {
     float w[NVR_KNN];
+    int idx[NVR_KNN];
     const float pdist = nvr_knn_weights(k, w);
-    for (int j = 0; j < NVR_JOINTS; ++j) bw[j] = nvr_blend_joint(k.idx, w, pbw_part, j);
+    for (int i = 0; i < NVR_KNN; ++i) idx[i] = nvr_knn_idx(k, i);
+    for (int j = 0; j < NVR_JOINTS; ++j) bw[j] = nvr_blend_joint(idx, w, pbw_part, j);
     return pdist;
 }
 

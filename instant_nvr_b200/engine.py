@@ -55,6 +55,8 @@ class Engine:
         self._params_keep = None
         self._frame_key = None
         self._frame_keep = None
+        self._topo_src = None
+        self._topo_key = 0
         self._ws: Optional[torch.Tensor] = None
         self._io: Optional[torch.Tensor] = None
 
@@ -106,10 +108,12 @@ class Engine:
         self._params_key, self._params_keep = key, tensors
 
     # ---- frame --------------------------------------------------------------------------------
-    def bind_frame(self, batch: Dict) -> None:
+    def bind_frame(self, batch: Dict, force: bool = False) -> None:
+        """Per-frame preparation (distance volume, KD vertex clusters).  Cached on the identity of the frame
+        tensors; ``force`` re-runs it (what a new frame costs)."""
         src = [batch[k] for k in _FRAME_KEYS]
         key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in src)
-        if key == self._frame_key:
+        if key == self._frame_key and not force:
             return
         dev = self.device
         t = {k: batch[k] for k in _FRAME_KEYS}
@@ -140,6 +144,12 @@ class Engine:
         F.A, F.big_A = keep["A"].data_ptr(), keep["big_A"].data_ptr()
         F.tuv, F.tbounds = keep["tuv"].data_ptr(), keep["tbounds"].data_ptr()
         F.frame_dim, F.latent_index = keep["frame_dim"].data_ptr(), keep["latent_index"].data_ptr()
+        # same subject / same part split => the KD vertex partition of the previous frame is reused
+        lkey = (t["lengths2"].data_ptr(), t["lengths2"]._version)
+        if lkey != self._topo_src:
+            self._topo_src = lkey
+            self._topo_key = (hash((int(F.maxlen),) + tuple(int(v) for v in t["lengths2"][0].tolist())) & 0x7FFFFFFFFFFFFFFF) | 1
+        F.topology_key = self._topo_key
         self._check(self.lib.nvr_bind_frame(self._h, C.byref(F), _stream_ptr()), "nvr_bind_frame")
         self._frame_key, self._frame_keep = key, keep
 

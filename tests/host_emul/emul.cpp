@@ -63,33 +63,38 @@ void emul_ray_points(const float* ray_o, const float* ray_d, const float* near_,
         }
 }
 
-// Host restatement of k_cluster_verts (Morton sort over the part bbox, clusters of NVR_CL, AABBs).
+// Host restatement of k_cluster_verts: balanced KD partition into clusters of NVR_CL (median split along
+// the longest axis, left half rounded to whole clusters; ties by vertex index), one AABB per cluster.
 struct HostClusters { std::vector<float4> verts, lo, hi; };
 static float idx_bits(int j) { float f; memcpy(&f, &j, 4); return f; }
+static void kd_split(const float* src, std::vector<int>& ids, int a, int b) {     // [a, b) in clusters
+    if (b - a <= 1) return;
+    const int i0 = a * NVR_CL, i1 = std::min<int>((int)ids.size(), b * NVR_CL);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = i0; i < i1; ++i)
+        for (int x = 0; x < 3; ++x) { lo[x] = fminf(lo[x], src[ids[i] * 3 + x]); hi[x] = fmaxf(hi[x], src[ids[i] * 3 + x]); }
+    int ax = 0;
+    float best = -1.0f;
+    for (int x = 0; x < 3; ++x) if (hi[x] - lo[x] > best) { best = hi[x] - lo[x]; ax = x; }
+    std::sort(ids.begin() + i0, ids.begin() + i1, [&](int p, int q) {
+        const float fp = src[p * 3 + ax], fq = src[q * 3 + ax];
+        return fp < fq || (fp == fq && p < q);
+    });
+    const int mid = a + (b - a) / 2;
+    kd_split(src, ids, a, mid);
+    kd_split(src, ids, mid, b);
+}
 static HostClusters build_clusters(const float* src, int n) {
     HostClusters hc;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int j = 0; j < n; ++j)
-        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], src[j * 3 + a]); hi[a] = fmaxf(hi[a], src[j * 3 + a]); }
-    std::vector<unsigned long long> keys(n);
-    for (int j = 0; j < n; ++j) {
-        unsigned code = 0;
-        for (int a = 0; a < 3; ++a) {
-            const float ext = hi[a] - lo[a];
-            float t = ext > 0.0f ? (src[j * 3 + a] - lo[a]) / ext : 0.0f;
-            int q = (int)(t * 1024.0f);
-            q = q < 0 ? 0 : (q > 1023 ? 1023 : q);
-            for (int b = 0; b < 10; ++b) code |= ((unsigned)(q >> b) & 1u) << (3 * b + a);
-        }
-        keys[j] = ((unsigned long long)code << 32) | (unsigned)j;
-    }
-    std::sort(keys.begin(), keys.end());
     const int ncl = (n + NVR_CL - 1) / NVR_CL;
+    std::vector<int> ids(n);
+    for (int j = 0; j < n; ++j) ids[j] = j;
+    kd_split(src, ids, 0, ncl);
     hc.verts.assign((size_t)ncl * NVR_CL, float4{INFINITY, INFINITY, INFINITY, idx_bits(0)});
     hc.lo.assign(ncl, float4{INFINITY, INFINITY, INFINITY, 0.f});
     hc.hi.assign(ncl, float4{-INFINITY, -INFINITY, -INFINITY, 0.f});
     for (int i = 0; i < n; ++i) {
-        const int j = (int)(keys[i] & 0xffffffffull), c = i / NVR_CL;
+        const int j = ids[i], c = i / NVR_CL;
         hc.verts[i] = float4{src[j * 3], src[j * 3 + 1], src[j * 3 + 2], idx_bits(j)};
         hc.lo[c].x = fminf(hc.lo[c].x, src[j * 3]); hc.hi[c].x = fmaxf(hc.hi[c].x, src[j * 3]);
         hc.lo[c].y = fminf(hc.lo[c].y, src[j * 3 + 1]); hc.hi[c].y = fmaxf(hc.hi[c].y, src[j * 3 + 1]);
@@ -133,7 +138,7 @@ void emul_knn_lbs(const float* part_pts, const float* part_pbw, const long long*
                 for (int c = 0; c < ncl; ++c) {
                     if (c == seed) continue;
                     const float lb = nvr_aabb_lb(hc.lo[c], hc.hi[c], p);
-                    if (!(lb * NVR_PRUNE_SLACK > k.d2[3])) { nvr_knn_scan(hc.verts.data() + (size_t)c * NVR_CL, NVR_CL, p, k); ++scanned; }
+                    if (!(lb * NVR_PRUNE_SLACK > nvr_knn_d2(k, 3))) { nvr_knn_scan(hc.verts.data() + (size_t)c * NVR_CL, NVR_CL, p, k); ++scanned; }
                 }
             }
             float bw[NVR_JOINTS];
@@ -144,7 +149,7 @@ void emul_knn_lbs(const float* part_pts, const float* part_pbw, const long long*
             for (int j = 0; j < NVR_JOINTS; ++j) bw_out[o * NVR_JOINTS + j] = bw[j];
             pdist_out[o] = pd;
             for (int a = 0; a < 3; ++a) { x0_out[o * 3 + a] = x0[a]; v_out[o * 3 + a] = v[a]; }
-            if (idx_out) for (int q = 0; q < NVR_KNN; ++q) idx_out[o * NVR_KNN + q] = k.idx[q];
+            if (idx_out) for (int q = 0; q < NVR_KNN; ++q) idx_out[o * NVR_KNN + q] = nvr_knn_idx(k, q);
         }
     }
     if (scanned_out) *scanned_out = scanned;

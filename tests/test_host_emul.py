@@ -201,9 +201,9 @@ def test_knn_lbs(emul, golden_setup):
                       fp(bw_c), fp(pd_c), fp(x0_c), fp(v_c), C.c_int(1), fp(idx_cl), C.byref(scanned))
     assert torch.equal(idx_bf, idx_cl)
     assert torch.equal(bw, bw_c) and torch.equal(pd, pd_c) and torch.equal(x0, x0_c)
-    total_clusters = int(sum((int(c) + 31) // 32 for c in ln)) * n
+    total_clusters = int(sum((int(c) + 15) // 16 for c in ln)) * n
     print(f"[knn] clusters scanned {scanned.value} of {total_clusters} ({scanned.value / total_clusters:.3f})")
-    assert scanned.value < 0.35 * total_clusters
+    assert scanned.value < 0.25 * total_clusters
     rbw, rpd = O.knn_blend_weights(q, pp, pw, ln)
     assert torch.allclose(bw, rbw, atol=1e-6, rtol=1e-5), (bw - rbw).abs().max()
     assert torch.allclose(pd, rpd, atol=1e-6, rtol=1e-5)
