@@ -305,7 +305,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
         { StageTimer t(h, st, NVR_STAGE_EMBED);
-        k_embed<<<grid_for(n, 256, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
+        k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
                                                          el, NVR_EMB_STRIDE); }
         StageTimer t(h, st, NVR_STAGE_MLP);
         if (tc)
@@ -427,7 +427,7 @@ extern "C" int nvr_embed_part(NvrHandle h, int32_t part, const float* xyz, int64
     if (n == 0) return 0;
     if (n >= (1ll << 31)) return fail(h, "nvr_embed_part: n must be < 2^31");
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
-    k_embed<<<grid_for(n, 256, h->sm_count * 2), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
+    k_embed<<<grid_for(n, 128, h->sm_count * 2), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return 0;

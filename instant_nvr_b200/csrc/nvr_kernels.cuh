@@ -479,14 +479,12 @@ k_deformer(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ 
 }
 
 // -----------------------------------------------------------------------------------------
-// THE gather: part grid embedding, one 64-byte row = two 256-bit loads per lane
+// THE gather: part grid embedding, one 32-byte sector per lane
 // -----------------------------------------------------------------------------------------
-// One lane = one point (32 points per warp): a grid entry is one 64-byte row of 16 fp32 features = two
-// 32-byte sectors, fetched with two 256-bit loads (LDG.E.256), so every byte of every sector that moves
-// is used and the per-point index arithmetic is paid once per point.  The 8 corners of a level go in
-// two batches of four (8 independent 32-byte loads in flight per lane).  Per corner the 16 features are
-// tree-summed and scaled by the trilinear weight (sum_c w_c sum_f t[c][f], the reference's
-// sum_f sum_c w_c t[c][f] re-associated).
+// A warp works on 16 points at a time: lane = 2*point + half.  A grid entry is one 64-byte row of 16
+// fp32 features = two 32-byte sectors; each lane fetches ONE whole sector with a single 256-bit load
+// (LDG.E.256), so every byte of every sector that moves is used and the per-point index arithmetic is
+// shared by only two lanes.  The 8 corner loads of a level are independent and issued back to back.
 // The level loop is deliberately NOT unrolled: unrolled, the kernel is ~10k instructions and spends
 // most of its time waiting for instruction fetch (profiles/r1a: 62 % stall_no_inst); rolled it is a
 // few hundred instructions that stay in the instruction cache.
@@ -495,7 +493,7 @@ k_deformer(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ 
 struct __align__(32) Sector { float v[8]; };
 __device__ __forceinline__ Sector ld_sector(const float* p) {
     Sector r;
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
                  : "l"(p));
     return r;
@@ -515,15 +513,19 @@ __global__ void __launch_bounds__(256, 2)
 k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
         float* __restrict__ eb, int emb_stride) {
     const int n = count_dev ? *count_dev : n_imm;
+    const int lane = threadIdx.x & 31, half = lane & 1;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool fast_mod = g.T_magic40 != 0;
     const unsigned int T32 = (unsigned int)g.T;
-    for (int pt = blockIdx.x * blockDim.x + threadIdx.x; pt < n; pt += gridDim.x * blockDim.x) {
-        const float* xp = xb + (long long)pt * xstride;
+    for (int base = warp * 16; base < n; base += n_warps * 16) {
+        const int pt = base + (lane >> 1);
+        const bool live = pt < n;
+        const float* xp = xb + (long long)(live ? pt : n - 1) * xstride;
         const float x[3] = {xp[0], xp[1], xp[2]};
         float u[3];
         nvr_normalise(g, x, u);
         float* o = eb + (long long)pt * emb_stride;
-        o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+        if (live && half == 0) { o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; }
 #pragma unroll 1
         for (int l = 0; l < g.n_levels; ++l) {
             const int res = g.res[l];
@@ -555,28 +557,22 @@ k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restr
                     row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
                 }
             }
+            Sector v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = ld_sector(tab + (unsigned long long)row[c] * 16 + half * 8);
             const float wx[2] = {1.0f - of[0], of[0]}, wy[2] = {1.0f - of[1], of[1]}, wz[2] = {1.0f - of[2], of[2]};
-            float lev = 0.0f;
+            float acc[8];
 #pragma unroll
-            for (int cb = 0; cb < 8; cb += 4) {
-                Sector v[4][2];
+            for (int f = 0; f < 8; ++f) acc[f] = 0.0f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float* r = tab + (unsigned long long)row[cb + c] * 16;
-                    v[c][0] = ld_sector(r);
-                    v[c][1] = ld_sector(r + 8);
-                }
+            for (int c = 0; c < 8; ++c) {
+                const float w = (wx[(c >> 2) & 1] * wy[(c >> 1) & 1]) * wz[c & 1];      // :158-159
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float* a = v[c][0].v;
-                    const float* b = v[c][1].v;
-                    const float sf = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) +
-                                     (((b[0] + b[1]) + (b[2] + b[3])) + ((b[4] + b[5]) + (b[6] + b[7])));   // :165
-                    const int cc = cb + c;
-                    lev += ((wx[(cc >> 2) & 1] * wy[(cc >> 1) & 1]) * wz[cc & 1]) * sf;                      // :158-160
-                }
+                for (int f = 0; f < 8; ++f) acc[f] += w * v[c].v[f];                    // :160
             }
-            o[3 + l] = lev;
+            float sfeat = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            sfeat += __shfl_xor_sync(0xffffffffu, sfeat, 1);                            // :165 sum over the 16 features
+            if (live && half == (l & 1)) o[3 + l] = sfeat;
         }
     }
 }

@@ -45,11 +45,11 @@ def assemble(local: torch.Tensor, n_rays: int, rank: int, world: int, tile: int 
         out = local.new_empty(world * cap, C)
         dist.all_gather_into_tensor(out, buf, group=group)
         gathered = out.view(world, cap, C)
-    frame = local.new_zeros(n_rays, C)
-    for r in range(world):
-        idx = shard_indices(n_rays, r, world, tile).to(local.device)
-        frame[idx] = gathered[r, : idx.shape[0]]
-    return frame
+    # tile k*world + r of the frame is tile k of rank r's shard: one permute, no per-rank scatter
+    # (only the last global tile can be partial, and it is the last tile of its rank, so the zero
+    # padding always falls past n_rays)
+    tiles = gathered.view(world, cap // tile, tile, C).permute(1, 0, 2, 3).reshape(-1, C)
+    return tiles[:n_rays].contiguous()
 
 
 def render_sharded(render_fn, ray_o, ray_d, near, far, rank: int, world: int, tile: int = 1024, group=None
