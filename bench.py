@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the supplementary training-step measurement")
     return ap.parse_args()
 
 
@@ -211,6 +212,51 @@ def mlp_tensor_report(prof):
                     "not by the MMAs"}
 
 
+def train_step_report(net, gframe, frame, n_rays=1024, n_samples=64, steps=10):
+    """BASELINE.json configs[2]: one training step = Renderer.render in training mode on 1024 rays x 64 samples
+    (stratified jitter, pair + distortion regularisers) + image loss + backward + Adam step, full-size tables."""
+    import dataclasses
+    from instant_nvr_b200.renderer import Renderer
+    from instant_nvr_b200.synthetic import make_rays
+    cfg0 = net.cfg
+    net.cfg = dataclasses.replace(cfg0, N_samples=n_samples, perturb=1.0, use_reg_distortion=True)
+    try:
+        rays = make_rays(frame, 32, 32)
+        batch = {**gframe, **{k: v.cuda() for k, v in rays.items()}}
+        target = torch.rand(1, n_rays, 3, device="cuda")
+        params = [p for p in net.parameters() if p.requires_grad]
+        opt = torch.optim.Adam(params, lr=5e-4, eps=1e-15)
+        r = Renderer(net)
+        net.train()
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            ret = r.render(dict(batch))
+            loss = ((ret["rgb_map"] - target) ** 2).mean() + 0.1 * ret["reg_distortion_loss"].mean() \
+                + 0.1 * torch.norm(ret["resd"], dim=2).mean()
+            if ret["oresd"].numel():
+                loss = loss + 0.01 * (ret["oresd"] ** 2).mean()
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"workload": f"training step, {n_rays} rays x {n_samples} samples, fwd + bwd + Adam on 286 M parameters",
+                "ms_per_step": ms, "ray_samples_per_sec": n_rays * n_samples / (ms * 1e-3),
+                "note": "backward returns dense gradients like the reference's autograd (1.14 GB zero-fill + scatter); "
+                        "Adam is torch.optim.Adam (library), everything else runs in libnvr_b200.so"}
+    finally:
+        net.eval()
+        net.cfg = cfg0
+
+
 def cpu_state_dict(seed=0):
     from instant_nvr_b200.config import PathConfig
     from instant_nvr_b200.network import Network
@@ -367,6 +413,9 @@ def main():
     if rank == 0:
         uniform = gather_uniform_roofline(eng, net, peak)
 
+    train_rep = None
+    if rank == 0 and world == 1 and not args.no_train:
+        train_rep = train_step_report(net, gframe, frame)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd_cpu = {k: v.detach().cpu() for k, v in net.state_dict().items()}
@@ -394,6 +443,7 @@ def main():
             "roofline": roofline,
             "roofline_uniform": uniform,
             "mlp_tensor": mlp_tensor_report(prof),
+            "train_step": train_rep,
             "stage_ms_per_step": {k: per_step(v) for k, v in prof["ms"].items()}, "stage_share": stage_share,
             "cpu_baseline": cpu_base,
         }

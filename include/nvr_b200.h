@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 3
+#define NVR_ABI_VERSION 4
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -179,6 +179,45 @@ int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const float* dirs,
  * All n points must fit one pass. */
 int nvr_query_points_debug(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw,
                            int32_t* surv_of_sample, float* warp_dbg, void* workspace, size_t ws_bytes, void* stream);
+
+/* ==================== training ====================
+ * Network.forward in training mode (inb_part_network_multiassign.py:126-168 with self.training) and its
+ * backward.  All n points are processed in ONE pass (the workspace must hold n points) and the workspace
+ * must stay untouched between nvr_train_forward and the matching nvr_train_backward: it holds the
+ * survivor / pair lists and embeddings the backward needs.
+ *
+ * Outputs besides raw (n,4) / occ (n): per SURVIVOR SLOT s < n_survivors (order = compaction order, not
+ * sample order; sample_of_slot (n) maps a slot back to its sample index):
+ *   x0 (n,5,3)   big-pose point before the residual (= ret['tpts'] rows s*5+p; zeros where the part is unflagged)
+ *   resd (n,5,3) deformer residual (= ret['resd']; zeros where unflagged)
+ *   tocc (n,5)   per-part occupancy (= ret['tocc']; zeros where unflagged)
+ * The survivor count is read with nvr_read_counters after the call. */
+int nvr_train_forward(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw, float* occ,
+                      float* x0, float* resd, float* tocc, int32_t* sample_of_slot,
+                      void* workspace, size_t ws_bytes, void* stream);
+
+/* Bytes of extra scratch nvr_train_backward needs for a forward of n points. */
+size_t nvr_train_scratch_bytes(NvrHandle h, int64_t n);
+
+/* Backward of nvr_train_forward.  d_raw (n,4): gradient of the scattered raw (add the gradient of `occ` into
+ * its 4th column: it is the same number).  d_resd (n,5,3) and d_tocc (n,5), slot order, may be NULL.
+ * `x0` is the forward's x0 output.  `grads` has the layout of NvrParams but every pointer is the gradient
+ * buffer of that tensor (same shape, fp32, ACCUMULATED into; NULL = not wanted); non-pointer fields are ignored.
+ * Gradient flow is the reference's: tables, MLPs, latent row, deformer; none through KNN / LBS / view dirs. */
+int nvr_train_backward(NvrHandle h, const float* d_raw, const float* d_resd, const float* d_tocc, const float* x0,
+                       int64_t n, const NvrParams* grads, void* workspace, size_t ws_bytes,
+                       void* scratch, size_t scratch_bytes, void* stream);
+
+/* Backward of nvr_deformer_residual (Network.resd on explicit points, used by the pair regulariser):
+ * tpts (n,3), d_resd (n,3) -> accumulates into grads->deformer_grid / deformer_mlp. */
+int nvr_deformer_backward(NvrHandle h, const float* tpts, const float* d_resd, int64_t n, const NvrParams* grads, void* stream);
+
+/* Alpha compositing on explicit raw (net_utils.py:12-44, epsilon = 0) and its backward: raw (n_rays,S,4) ->
+ * weights (n_rays,S), rgb_map (n_rays,3), acc_map (n_rays).  d_weights / d_rgb_map / d_acc_map may be NULL. */
+int nvr_composite_forward(NvrHandle h, const float* raw, int64_t n_rays, int32_t n_samples, float* weights,
+                          float* rgb_map, float* acc_map, void* stream);
+int nvr_composite_backward(NvrHandle h, const float* raw, int64_t n_rays, int32_t n_samples, const float* d_weights,
+                           const float* d_rgb_map, const float* d_acc_map, float* d_raw, void* stream);
 
 /* Per-stage device timing.  nvr_profile(h, 1) clears the accumulators and makes every later launch
  * record a CUDA-event pair on its stream; nvr_profile_read synchronises the device and sums them. */

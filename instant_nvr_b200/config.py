@@ -12,6 +12,7 @@ needs the reference tree.
 """
 from __future__ import annotations
 
+from functools import cached_property
 from dataclasses import dataclass, field, replace
 from typing import List, Sequence, Tuple
 
@@ -47,7 +48,8 @@ def next_prime(n: int) -> int:
 
 @dataclass(frozen=True)
 class GridSpec:
-    """One multi-resolution dense+hashed grid (part_base_embedder.py:13-104)."""
+    """One multi-resolution dense+hashed grid (part_base_embedder.py:13-104).  Derived quantities are cached
+    (the spec is frozen): next_prime by trial division must not run on every pointer-table rebuild."""
     n_levels: int = 16
     n_feat: int = 16
     log2_T: int = 18
@@ -57,20 +59,20 @@ class GridSpec:
     bbox: Tuple[Tuple[float, float, float], Tuple[float, float, float]] = ((0., 0., 0.), (1., 1., 1.))
     use_batch_bounds: bool = True      # bounds replaced from batch['bounds'] at iter_step == 1
 
-    @property
+    @cached_property
     def T(self) -> int:
         return next_prime(2 ** self.log2_T)
 
-    @property
+    @cached_property
     def res(self) -> List[int]:
         # int(base * b**i) in Python float64, exactly as part_base_embedder.py:52
         return [int(self.base_res * self.b ** i) for i in range(self.n_levels)]
 
-    @property
+    @cached_property
     def cnt(self) -> List[int]:
         return [r ** 3 for r in self.res]
 
-    @property
+    @cached_property
     def start_hash(self) -> int:
         # first level whose dense entry count exceeds the table size (part_base_embedder.py:63-67)
         T = self.T
@@ -79,15 +81,15 @@ class GridSpec:
                 return i
         return self.n_levels
 
-    @property
+    @cached_property
     def n_hash_levels(self) -> int:
         return self.n_levels - self.start_hash
 
-    @property
+    @cached_property
     def dense_rows(self) -> int:
         return sum(self.cnt[: self.start_hash])
 
-    @property
+    @cached_property
     def dense_offsets(self) -> List[int]:
         """Row offset of level l inside the packed ``dense`` table (entries_sum[l-1], :129)."""
         out, acc = [], 0
@@ -97,7 +99,7 @@ class GridSpec:
                 acc += self.cnt[l]
         return out
 
-    @property
+    @cached_property
     def out_dim(self) -> int:
         return 3 + (self.n_levels if self.sum_features else self.n_levels * self.n_feat)
 
@@ -134,6 +136,9 @@ class PathConfig:
     tpose_viewdir: bool = True
     aggr: str = ""
     perturb: float = 0.0
+    use_pair_reg: bool = True          # config.py defaults of the reference (lib/config/config.py)
+    use_reg_distortion: bool = False
+    use_freespace_loss: bool = False
 
     # ---- derived -----------------------------------------------------------------------
     @property
@@ -223,6 +228,8 @@ class PathConfig:
             view_res=int(cfg.viewdir_embedder.kwargs.res), d_hidden=int(cfg.network.occ.d_hidden),
             ps=tuple(int(v) for v in cfg.ps), chunk=int(cfg.chunk), render_chunk=int(cfg.render_chunk),
             tpose_viewdir=bool(cfg.tpose_viewdir), aggr=str(cfg.aggr), perturb=float(cfg.perturb),
+            use_pair_reg=bool(getattr(cfg, "use_pair_reg", True)), use_reg_distortion=bool(getattr(cfg, "use_reg_distortion", False)),
+            use_freespace_loss=bool(getattr(cfg, "use_freespace_loss", False)),
         )
         if cfg.part3 or cfg.part6 or cfg.part_deform:
             raise NotImplementedError("cfg.part3 / part6 / part_deform are outside the inb hot path")

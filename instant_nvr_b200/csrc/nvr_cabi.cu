@@ -13,6 +13,7 @@
 #include "../../include/nvr_b200.h"
 #include "nvr_kernels.cuh"
 #include "nvr_mlp_tc.cuh"
+#include "nvr_train.cuh"
 
 struct NvrEngine {
     NvrConfig cfg;
@@ -119,6 +120,8 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
         cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_CLUSTER_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_deformer_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES) != cudaSuccess ||
         cudaMalloc(&h->d_part_mlp, NVR_PARTS * sizeof(PartMlpDev)) != cudaSuccess ||
         cudaMalloc(&h->d_mlp_blocks, (size_t)NVR_PARTS * TC_BLOCK_FLOATS * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
@@ -282,7 +285,7 @@ static int grid_for(long long items, int per_block, int max_blocks) {
 // One pass over `n` samples (n <= ws.cap): cull -> warp -> 5x(embed, mlp).  The caller resolves.
 static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const float* ray_d, const float* near_,
                     const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
-                    float* dbg = nullptr) {
+                    float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr) {
     const int sm = h->sm_count;
     NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
     { StageTimer t(h, st, NVR_STAGE_CULL);
@@ -294,7 +297,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     k_knn<<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg); }
     { StageTimer t(h, st, NVR_STAGE_WARP);
     k_warp<<<dim3(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS), WARP_THREADS, 0, st>>>(
-        h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg); }
+        h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd); }
     const bool tc = h->cfg.mlp_mode == 1;
     if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
         StageTimer t(h, st, NVR_STAGE_MLP);
@@ -472,6 +475,139 @@ extern "C" int nvr_query_points_debug(NvrHandle h, const float* wpts, const floa
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return snapshot_counters(h, w, st);
+}
+
+// ---- training ----------------------------------------------------------------------------------
+__global__ void k_export_slots(const int* __restrict__ counters, const float4* __restrict__ surv, const float4* __restrict__ raws,
+                               float* __restrict__ tocc, int* __restrict__ sample_of_slot) {
+    const int n = counters[NVR_CTR_SURV];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        sample_of_slot[s] = __float_as_int(surv[s].w);
+#pragma unroll
+        for (int p = 0; p < NVR_PARTS; ++p) tocc[(long long)s * NVR_PARTS + p] = raws[(long long)s * NVR_PARTS + p].w;
+    }
+}
+
+extern "C" int nvr_train_forward(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw, float* occ,
+                                 float* x0, float* resd, float* tocc, int32_t* sample_of_slot, void* workspace, size_t ws_bytes,
+                                 void* stream_) {
+    if (int rc = ready(h, "nvr_train_forward")) return rc;
+    if (n < 0 || (n > 0 && (!wpts || !viewdir || !raw || !x0 || !resd || !tocc || !sample_of_slot)))
+        return fail(h, "nvr_train_forward: null argument");
+    Workspace w;
+    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_train_forward: workspace must hold all points in one pass");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream_;
+    NVR_CHECK(h, cudaMemsetAsync(x0, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
+    NVR_CHECK(h, cudaMemsetAsync(resd, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
+    NVR_CHECK(h, cudaMemsetAsync(tocc, 0, (size_t)n * NVR_NUM_PARTS * sizeof(float), st));
+    if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, nullptr, x0, resd)) return rc;
+    k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, n, (float4*)raw, occ);
+    k_export_slots<<<grid_for(n, 256, h->sm_count * 8), 256, 0, st>>>(w.counters, w.surv, w.raws, tocc, sample_of_slot);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches += 2;
+    return snapshot_counters(h, w, st);
+}
+
+// scratch of the backward: [gcount 64 B][glist 5*cap GradRec][d_emb 5*cap*20][d_x 5*cap*3][wl_x0 5*cap*3][wl_dr 5*cap*3]
+static size_t train_scratch_bytes(long long cap) {
+    return 256 + (size_t)cap * NVR_NUM_PARTS * (sizeof(GradRec) + (NVR_EMB_STRIDE + 9) * sizeof(float));
+}
+extern "C" size_t nvr_train_scratch_bytes(NvrHandle, int64_t n) { return train_scratch_bytes(((n < 1 ? 1 : n) + 63) & ~63ll); }
+
+static PartMlpGrad mlp_grad(const NvrPart& g, int n_rgb) {
+    PartMlpGrad o;
+    for (int i = 0; i < 2; ++i) o.occ[i] = LinearGrad{(float*)g.occ[i].weight, (float*)g.occ[i].bias};
+    for (int i = 0; i < 3; ++i) o.rgb[i] = i < n_rgb ? LinearGrad{(float*)g.rgb[i].weight, (float*)g.rgb[i].bias} : LinearGrad{nullptr, nullptr};
+    o.latent = (float*)g.rgb_latent;
+    return o;
+}
+static DeformerGrad deformer_grad(const NvrParams* g) {
+    return DeformerGrad{(float*)g->deformer_mlp[0].weight, (float*)g->deformer_mlp[0].bias, (float*)g->deformer_mlp[1].weight,
+                        (float*)g->deformer_mlp[1].bias, (float*)g->deformer_mlp[2].weight, (float*)g->deformer_mlp[2].bias};
+}
+
+extern "C" int nvr_train_backward(NvrHandle h, const float* d_raw, const float* d_resd, const float* d_tocc, const float* x0,
+                                  int64_t n, const NvrParams* grads, void* workspace, size_t ws_bytes, void* scratch,
+                                  size_t scratch_bytes, void* stream_) {
+    if (int rc = ready(h, "nvr_train_backward")) return rc;
+    if (n < 0 || !grads || (n > 0 && (!d_raw || !x0))) return fail(h, "nvr_train_backward: null argument");
+    Workspace w;
+    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_train_backward: not the forward's workspace");
+    if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < train_scratch_bytes(w.cap))
+        return fail(h, "nvr_train_backward: scratch too small (nvr_train_scratch_bytes) or not 256-byte aligned");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream_;
+    const long long cap = w.cap;
+    char* p = (char*)scratch;
+    int* gcount = (int*)p; p += 256;
+    GradRec* glist = (GradRec*)p; p += (size_t)cap * NVR_NUM_PARTS * sizeof(GradRec);
+    float* d_emb = (float*)p; p += (size_t)cap * NVR_NUM_PARTS * NVR_EMB_STRIDE * sizeof(float);
+    float* d_x = (float*)p; p += (size_t)cap * NVR_NUM_PARTS * 3 * sizeof(float);
+    float* wl_x0 = (float*)p; p += (size_t)cap * NVR_NUM_PARTS * 3 * sizeof(float);
+    float* wl_dr = (float*)p;
+    const int sm = h->sm_count;
+    NVR_CHECK(h, cudaMemsetAsync(gcount, 0, 64, st));
+    k_bwd_select<<<dim3(grid_for(n, 256, sm * 4), NVR_NUM_PARTS), 256, 0, st>>>(w.counters, w.pairs, (int)cap, w.surv, w.raws,
+                                                                              (const float4*)d_raw, d_tocc, glist, gcount);
+    k_bwd_resd_list<<<dim3(grid_for(n, 256, sm * 4), NVR_NUM_PARTS), 256, 0, st>>>(w.counters, w.pairs, (int)cap, x0, d_resd, wl_x0, wl_dr);
+    for (int pt = 0; pt < NVR_NUM_PARTS; ++pt) {
+        const NvrPart& gp = grads->part[pt];
+        const GradRec* gl = glist + (size_t)pt * cap;
+        const PairRec* pl = w.pairs + (size_t)pt * cap;
+        const float* el = w.emb + (size_t)pt * cap * NVR_EMB_STRIDE;
+        float* de = d_emb + (size_t)pt * cap * NVR_EMB_STRIDE;
+        float* dx = d_x + (size_t)pt * cap * 3;
+        k_mlp_bwd<<<grid_for(n, BT, sm), BTHREADS, MB_SMEM_BYTES, st>>>(h->part_mlp[pt], mlp_grad(gp, h->part_mlp[pt].n_rgb),
+                                                                       h->fdev.latent_index, gcount + pt, gl, pl, el, de);
+        k_embed_bwd<<<grid_for(n, 16, sm * 8), 256, 0, st>>>(h->part_grid[pt], GridGrad{(float*)gp.grid.dense, (float*)gp.grid.hash},
+                                                           gcount + pt, gl, pl, de, dx);
+        k_bwd_add_dx<<<grid_for(n, 256, sm * 2), 256, 0, st>>>(gcount + pt, gl, dx, wl_dr + (size_t)pt * cap * 3);
+        k_deformer_bwd<<<grid_for(n, BT, sm), BTHREADS, DB_SMEM_BYTES, st>>>(
+            h->fdev, h->def_grid, h->def_mlp, deformer_grad(grads), GridGrad{(float*)grads->deformer_grid.dense, (float*)grads->deformer_grid.hash},
+            wl_x0 + (size_t)pt * cap * 3, wl_dr + (size_t)pt * cap * 3, w.counters + NVR_CTR_PAIR + pt, 0);
+    }
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches += 2 + 4 * NVR_NUM_PARTS;
+    return 0;
+}
+
+extern "C" int nvr_deformer_backward(NvrHandle h, const float* tpts, const float* d_resd, int64_t n, const NvrParams* grads, void* stream_) {
+    if (int rc = ready(h, "nvr_deformer_backward")) return rc;
+    if (n < 0 || !grads || (n > 0 && (!tpts || !d_resd))) return fail(h, "nvr_deformer_backward: null argument");
+    if (n == 0) return 0;
+    if (n >= (1ll << 31)) return fail(h, "nvr_deformer_backward: n must be < 2^31");
+    k_deformer_bwd<<<grid_for(n, BT, h->sm_count), BTHREADS, DB_SMEM_BYTES, (cudaStream_t)stream_>>>(
+        h->fdev, h->def_grid, h->def_mlp, deformer_grad(grads), GridGrad{(float*)grads->deformer_grid.dense, (float*)grads->deformer_grid.hash},
+        tpts, d_resd, nullptr, (int)n);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" int nvr_composite_forward(NvrHandle h, const float* raw, int64_t n_rays, int32_t n_samples, float* weights, float* rgb_map,
+                                     float* acc_map, void* stream_) {
+    if (!h) return 1;
+    if (n_rays < 0 || n_samples < 1 || (n_rays > 0 && (!raw || !weights || !rgb_map || !acc_map))) return fail(h, "nvr_composite_forward: bad argument");
+    if (n_rays == 0) return 0;
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    k_composite_fwd<<<grid_for(n_rays, 128, h->sm_count * 8), 128, 0, (cudaStream_t)stream_>>>((const float4*)raw, n_rays, n_samples, weights, rgb_map, acc_map);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" int nvr_composite_backward(NvrHandle h, const float* raw, int64_t n_rays, int32_t n_samples, const float* d_weights,
+                                      const float* d_rgb_map, const float* d_acc_map, float* d_raw, void* stream_) {
+    if (!h) return 1;
+    if (n_rays < 0 || n_samples < 1 || (n_rays > 0 && (!raw || !d_raw))) return fail(h, "nvr_composite_backward: bad argument");
+    if (n_rays == 0) return 0;
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    k_composite_bwd<<<grid_for(n_rays, 128, h->sm_count * 8), 128, 0, (cudaStream_t)stream_>>>((const float4*)raw, n_rays, n_samples, d_weights,
+                                                                                             d_rgb_map, d_acc_map, (float4*)d_raw);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
 }
 
 extern "C" int nvr_profile(NvrHandle h, int32_t enable) {

@@ -431,7 +431,8 @@ __device__ __forceinline__ DeformerSmem stage_deformer(float* sm, const Deformer
 __global__ void __launch_bounds__(WARP_THREADS)
 k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs, int dir_div,
        const int* __restrict__ counters, const float4* __restrict__ surv, const KnnRec* __restrict__ recs,
-       PairRec* __restrict__ pairs, int cap, float* __restrict__ dbg) {
+       PairRec* __restrict__ pairs, int cap, float* __restrict__ dbg, float* __restrict__ out_x0, float* __restrict__ out_resd) {
+    // out_x0 / out_resd (training): (slots, 5, 3) big-pose point and residual of every flagged (survivor, part)
     __shared__ __align__(16) float sm[WARP_SMEM_FLOATS];
     const int part = blockIdx.y;
     const int n = counters[NVR_CTR_PAIR + part];
@@ -456,6 +457,11 @@ k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs
         out.vx = v[0]; out.vy = v[1]; out.vz = v[2];
         out.surv = rec.surv; out._pad = 0;
         pairs[(long long)part * cap + i] = out;
+        if (out_x0) {
+            const long long o3 = ((long long)rec.surv * NVR_PARTS + part) * 3;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { out_x0[o3 + a] = x0[a]; out_resd[o3 + a] = r[a]; }
+        }
         if (dbg) {
             float* dr = dbg + ((long long)sample * NVR_PARTS + part) * 8;
             dr[1] = out.x; dr[2] = out.y; dr[3] = out.z; dr[4] = v[0]; dr[5] = v[1]; dr[6] = v[2];

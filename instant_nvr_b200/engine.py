@@ -32,6 +32,43 @@ def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
 DEFAULT_MLP_MODE = 1
 
 
+def _params_struct(net, grads: Optional[Dict[str, torch.Tensor]] = None) -> "cabi.NvrParams":
+    """NvrParams over the module tree.  With ``grads`` (parameter name -> gradient buffer) the pointer fields hold the
+    gradient buffers instead (0 where absent), which is what nvr_train_backward / nvr_deformer_backward take."""
+    names = {id(p): n for n, p in net.named_parameters()}
+
+    def ptr(t):
+        if grads is None:
+            return t.data_ptr()
+        g = grads.get(names[id(t)])
+        return g.data_ptr() if g is not None else 0
+
+    def lin(m):
+        d = cabi.linear_desc(m)
+        d.weight, d.bias = ptr(m.weight), ptr(m.bias)
+        return d
+
+    def grid(e):
+        g = cabi.grid_desc(e)
+        g.dense, g.hash = ptr(e.dense), ptr(e.hash)
+        return g
+    P = cabi.NvrParams()
+    for i, part in enumerate(net.tpose_human.part_networks):
+        d = P.part[i]
+        d.grid = grid(part.embedder)
+        for k, m in enumerate(part.occ.linears):
+            d.occ[k] = lin(m)
+        for k, m in enumerate(part.rgb.linears):
+            d.rgb[k] = lin(m)
+        d.n_rgb = len(part.rgb.linears)
+        d.n_latent = part.rgb_latent.shape[0]
+        d.rgb_latent = ptr(part.rgb_latent)
+    P.deformer_grid = grid(net.tpose_deformer.embedder)
+    for k, idx in enumerate((0, 2, 4)):
+        P.deformer_mlp[k] = lin(net.tpose_deformer.mlp[idx])
+    return P
+
+
 class Engine:
     def __init__(self, cfg: PathConfig, device: Optional[torch.device] = None, max_points_per_pass: int = 8 << 20,
                  mlp_mode: Optional[int] = None):
@@ -90,20 +127,7 @@ class Engine:
                                    "(move the module with .cuda(); there is no CPU path)")
             if not p.is_contiguous():
                 raise RuntimeError(f"parameter {name} is not contiguous")
-        P = cabi.NvrParams()
-        for i, part in enumerate(net.tpose_human.part_networks):
-            d = P.part[i]
-            d.grid = cabi.grid_desc(part.embedder)
-            for k, lin in enumerate(part.occ.linears):
-                d.occ[k] = cabi.linear_desc(lin)
-            for k, lin in enumerate(part.rgb.linears):
-                d.rgb[k] = cabi.linear_desc(lin)
-            d.n_rgb = len(part.rgb.linears)
-            d.n_latent = part.rgb_latent.shape[0]
-            d.rgb_latent = part.rgb_latent.data_ptr()
-        P.deformer_grid = cabi.grid_desc(net.tpose_deformer.embedder)
-        for k, idx in enumerate((0, 2, 4)):
-            P.deformer_mlp[k] = cabi.linear_desc(net.tpose_deformer.mlp[idx])
+        P = _params_struct(net)
         self._check(self.lib.nvr_bind_params(self._h, C.byref(P)), "nvr_bind_params")
         self._params_key, self._params_keep = key, tensors
 
@@ -232,6 +256,67 @@ class Engine:
         self._check(self.lib.nvr_part_mlp(self._h, int(part), e20.data_ptr(), dirs.data_ptr(), n, raw.data_ptr(), ws, ws_bytes,
                                           _stream_ptr()), "nvr_part_mlp")
         return raw
+
+    # ---- training ---------------------------------------------------------------------------------
+    def train_forward(self, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict) -> Dict:
+        """nvr_train_forward on all points in one pass.  Returns the outputs plus the private workspace the
+        backward needs (kept alive by the returned dict)."""
+        self.bind_frame(batch)
+        wpts, viewdir = _dev_f32(wpts, self.device), _dev_f32(viewdir, self.device)
+        n = wpts.shape[0]
+        dev, f32 = self.device, torch.float32
+        st = {"raw": torch.empty(n, 4, dtype=f32, device=dev), "occ": torch.empty(n, dtype=f32, device=dev),
+              "x0": torch.empty(n, 5, 3, dtype=f32, device=dev), "resd": torch.empty(n, 5, 3, dtype=f32, device=dev),
+              "tocc": torch.empty(n, 5, dtype=f32, device=dev), "sample_of_slot": torch.empty(n, dtype=torch.int32, device=dev),
+              "ws": torch.empty(int(self.lib.nvr_workspace_bytes(self._h, max(n, 64))), dtype=torch.uint8, device=dev),
+              "n": n, "batch": batch}
+        self._check(self.lib.nvr_train_forward(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, st["raw"].data_ptr(),
+                                               st["occ"].data_ptr(), st["x0"].data_ptr(), st["resd"].data_ptr(),
+                                               st["tocc"].data_ptr(), st["sample_of_slot"].data_ptr(), st["ws"].data_ptr(),
+                                               st["ws"].numel(), _stream_ptr()), "nvr_train_forward")
+        st["n_surv"] = int(self.counters()["n_survivors"]) if n else 0      # one host sync (the reference has seven)
+        return st
+
+    def train_backward(self, st: Dict, d_raw: torch.Tensor, d_resd, d_tocc, net, grads: Dict[str, torch.Tensor]) -> None:
+        self.bind_params(net)
+        self.bind_frame(st["batch"])
+        n = st["n"]
+        scratch = torch.empty(int(self.lib.nvr_train_scratch_bytes(self._h, max(n, 64))), dtype=torch.uint8, device=self.device)
+        G = _params_struct(net, grads)
+        ptr = lambda t: 0 if t is None else _dev_f32(t, self.device).data_ptr()
+        d_raw = _dev_f32(d_raw, self.device)
+        keep = [_dev_f32(t, self.device) for t in (d_resd, d_tocc) if t is not None]
+        self._check(self.lib.nvr_train_backward(self._h, d_raw.data_ptr(), ptr(d_resd), ptr(d_tocc), st["x0"].data_ptr(), n,
+                                                C.byref(G), st["ws"].data_ptr(), st["ws"].numel(), scratch.data_ptr(),
+                                                scratch.numel(), _stream_ptr()), "nvr_train_backward")
+        del keep
+
+    def deformer_backward(self, tpts: torch.Tensor, d_resd: torch.Tensor, batch: Dict, net, grads: Dict[str, torch.Tensor]) -> None:
+        self.bind_params(net)
+        self.bind_frame(batch)
+        tpts, d_resd = _dev_f32(tpts.reshape(-1, 3), self.device), _dev_f32(d_resd.reshape(-1, 3), self.device)
+        G = _params_struct(net, grads)
+        self._check(self.lib.nvr_deformer_backward(self._h, tpts.data_ptr(), d_resd.data_ptr(), tpts.shape[0], C.byref(G),
+                                                   _stream_ptr()), "nvr_deformer_backward")
+
+    def composite_forward(self, raw: torch.Tensor):
+        raw = _dev_f32(raw, self.device)
+        R, S = raw.shape[:2]
+        w = torch.empty(R, S, dtype=torch.float32, device=self.device)
+        rgb = torch.empty(R, 3, dtype=torch.float32, device=self.device)
+        acc = torch.empty(R, dtype=torch.float32, device=self.device)
+        self._check(self.lib.nvr_composite_forward(self._h, raw.data_ptr(), R, S, w.data_ptr(), rgb.data_ptr(), acc.data_ptr(),
+                                                   _stream_ptr()), "nvr_composite_forward")
+        return w, rgb, acc
+
+    def composite_backward(self, raw: torch.Tensor, d_w, d_rgb, d_acc) -> torch.Tensor:
+        raw = _dev_f32(raw, self.device)
+        R, S = raw.shape[:2]
+        d_raw = torch.empty(R, S, 4, dtype=torch.float32, device=self.device)
+        ts = [None if t is None else _dev_f32(t, self.device) for t in (d_w, d_rgb, d_acc)]
+        self._check(self.lib.nvr_composite_backward(self._h, raw.data_ptr(), R, S, *[0 if t is None else t.data_ptr() for t in ts],
+                                                    d_raw.data_ptr(), _stream_ptr()), "nvr_composite_backward")
+        return d_raw
 
     def query_points_debug(self, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict):
         """query_points + per-stage taps: raw (N,4), surv_of_sample (N,), warp (N,5,8)=[flag,x,y,z,vx,vy,vz,pdist]."""

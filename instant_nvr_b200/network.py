@@ -60,12 +60,12 @@ class Network(nn.Module):
     def forward(self, wpts: torch.Tensor, viewdir: torch.Tensor, dists: torch.Tensor, batch: Dict):
         """wpts, viewdir (N,3) f32 world-space sample points / unit view directions; ``dists`` is
         accepted and ignored exactly as the reference does (part_base_network.py:44-63 never reads
-        it).  Returns {'raw': (1,N,4) = [r,g,b,occ], 'occ': (1,N,1)}."""
-        if self.training:
-            raise NotImplementedError(
-                "training-mode forward (resd / tpts / tocc + autograd) is SURVEY.md section 8(f) item 1; "
-                "this build provides the eval path only")
+        it).  Returns {'raw': (1,N,4) = [r,g,b,occ], 'occ': (1,N,1)}; in training mode also resd / tpts / tocc."""
         self._maybe_update_bounds(batch)
+        if self.training:
+            # + 'resd' (1,N',5,3), 'tpts' (1,5N',3), 'tocc' (1,5N',1), all attached to autograd (:161-165)
+            from .training import network_train_forward
+            return network_train_forward(self, wpts, viewdir, batch)
         raw, occ = self.engine().query_points(wpts, viewdir, batch)
         return {"raw": raw[None], "occ": occ[None]}
 
@@ -73,11 +73,14 @@ class Network(nn.Module):
         """Deformer residual at canonical points (B,N,3) -> (B,N,3)
         (inb_part_network_multiassign.py:122-124)."""
         B, N, D = tpts.shape
+        if self.training and torch.is_grad_enabled():
+            from .training import deformer_train
+            return deformer_train(self, tpts, batch)
         return self.engine().deformer_residual(tpts.reshape(-1, 3), batch).view(B, N, D)
 
     def _maybe_update_bounds(self, batch: Dict) -> None:
         # part_base_embedder.py:107-109: at training iter 1 the part bboxes are replaced by the
-        # data-derived ones; kept for state_dict fidelity although training itself is not built yet.
+        # data-derived ones.
         if "iter_step" in batch and batch["iter_step"] == 1 and "bounds" in batch:
             with torch.no_grad():
                 for pid, part in enumerate(self.tpose_human.part_networks):

@@ -27,9 +27,9 @@ class Renderer:
         ``return_raw``, raw (1,R*S,4), occ (1,R*S,1)."""
         net = self.net
         if net.training:
-            raise NotImplementedError(
-                "training-mode render (stratified jitter, pair / distortion regularisers, autograd) is "
-                "SURVEY.md section 8(f) item 1; this build provides the eval path only")
+            from .training import render_train
+            net._maybe_update_bounds(batch)
+            return render_train(self, batch, epoch)
         if epoch != -1:
             batch["epoch"] = epoch
         ray_o, ray_d, near, far = batch["ray_o"], batch["ray_d"], batch["near"], batch["far"]

@@ -1,0 +1,168 @@
+"""Training-mode surfaces of the drop-in Network / Renderer: autograd glue over the C-ABI training entry
+points (``nvr_train_forward`` / ``nvr_train_backward`` / ``nvr_deformer_backward`` / ``nvr_composite_*``).
+
+Mirrors what the reference's autograd gives for ``Network.forward`` with ``self.training``
+(``inb_part_network_multiassign.py:126-168``), ``Network.resd`` (``:122-124``) and ``volume_rendering``
+(``lib/utils/net_utils.py:12-44``): gradients reach the part grids, the part MLPs, the frame's latent row, the
+deformer MLP and the deformer grid -- and nothing else (KNN weights / blended transforms / view directions are
+constants of the frame, ``:85-90``).  All arithmetic is in the CUDA library; this file only moves pointers.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+
+
+def trainable(net) -> List[Tuple[str, torch.nn.Parameter]]:
+    """The reference's trainable tensors in a fixed order (dense, hash, MLP weights/biases,
+    rgb_latent; every other state_dict entry is a frozen buffer)."""
+    return [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+
+
+class _NetworkTrainFn(torch.autograd.Function):
+    """raw (N,4), occ (N,1), resd (Ns,5,3), tocc (Ns,5) [differentiable]; x0 (Ns,5,3), sample_of_slot (Ns) [constants].
+    Slot order (compaction order) on this level; the caller re-orders to the reference's sample order."""
+
+    @staticmethod
+    def forward(ctx, net, batch, wpts, viewdir, *params):
+        eng = net.engine()
+        state = eng.train_forward(wpts, viewdir, batch)
+        ctx.net, ctx.state = net, state
+        ctx.names = [n for n, _ in trainable(net)]
+        ns = state["n_surv"]
+        outs = (state["raw"], state["occ"][:, None], state["resd"][:ns], state["tocc"][:ns], state["x0"][:ns],
+                state["sample_of_slot"][:ns])
+        ctx.mark_non_differentiable(outs[4], outs[5])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_raw, d_occ, d_resd, d_tocc, _dx0, _dsos):
+        net, state = ctx.net, ctx.state
+        eng = net.engine()
+        n, ns = state["raw"].shape[0], state["n_surv"]
+        g_raw = torch.zeros(n, 4, dtype=torch.float32, device=state["raw"].device) if d_raw is None else d_raw.contiguous().clone()
+        if d_occ is not None:
+            g_raw[:, 3] += d_occ[:, 0]                       # 'occ' is the 4th column of the fused raw (:254-255)
+
+        def slots(g, tail):
+            if g is None:
+                return None
+            full = torch.zeros((n,) + tail, dtype=torch.float32, device=g.device)
+            full[:ns] = g
+            return full
+        params = dict(trainable(net))
+        grads = {name: torch.zeros_like(params[name]) for name in ctx.names}
+        eng.train_backward(state, g_raw, slots(d_resd, (5, 3)), slots(d_tocc, (5,)), net, grads)
+        ctx.state = None
+        return (None, None, None, None) + tuple(grads[name] for name in ctx.names)
+
+
+def network_train_forward(net, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict) -> Dict[str, torch.Tensor]:
+    """``Network.forward`` with ``self.training``: {'raw' (1,N,4), 'occ' (1,N,1), 'resd' (1,N',5,3),
+    'tpts' (1,5N',3), 'tocc' (1,5N',1)} with survivors in the reference's order (ascending sample index)."""
+    params = [p for _, p in trainable(net)]
+    raw, occ, resd, tocc, x0, sos = _NetworkTrainFn.apply(net, batch, wpts, viewdir, *params)
+    order = torch.argsort(sos.long())                        # compaction order -> nonzero() order (:137)
+    resd, tocc, x0 = resd[order], tocc[order], x0[order]
+    return {"raw": raw[None], "occ": occ[None], "resd": resd[None], "tpts": x0.reshape(1, -1, 3),
+            "tocc": tocc.reshape(1, -1, 1)}
+
+
+class _DeformerFn(torch.autograd.Function):
+    """Network.resd on explicit canonical points; gradient to the deformer's parameters only (the points are
+    constants of the step: the pair regulariser's jittered neighbours, inb_renderer.py:78-94)."""
+
+    @staticmethod
+    def forward(ctx, net, batch, tpts, *params):
+        eng = net.engine()
+        ctx.net, ctx.batch = net, batch
+        ctx.names = [n for n, _ in trainable(net) if n.startswith("tpose_deformer.")]
+        pts = tpts.detach().reshape(-1, 3).contiguous()
+        ctx.save_for_backward(pts)
+        return eng.deformer_residual(pts, batch)
+
+    @staticmethod
+    def backward(ctx, d_resd):
+        (pts,) = ctx.saved_tensors
+        net = ctx.net
+        params = dict(trainable(net))
+        grads = {name: torch.zeros_like(params[name]) for name in ctx.names}
+        net.engine().deformer_backward(pts, d_resd.contiguous(), ctx.batch, net, grads)
+        return (None, None, None) + tuple(grads[name] for name in ctx.names)
+
+
+def deformer_train(net, tpts: torch.Tensor, batch: Dict) -> torch.Tensor:
+    B, N, D = tpts.shape
+    params = [p for n, p in trainable(net) if n.startswith("tpose_deformer.")]
+    return _DeformerFn.apply(net, batch, tpts, *params).view(B, N, D)
+
+
+class _CompositeFn(torch.autograd.Function):
+    """volume_rendering(rgb, occ, epsilon=0): raw (R,S,4) -> weights (R,S), rgb_map (R,3), acc_map (R)."""
+
+    @staticmethod
+    def forward(ctx, eng, raw):
+        raw = raw.contiguous()
+        ctx.eng = eng
+        ctx.save_for_backward(raw)
+        return eng.composite_forward(raw)
+
+    @staticmethod
+    def backward(ctx, d_weights, d_rgb_map, d_acc_map):
+        (raw,) = ctx.saved_tensors
+        return None, ctx.eng.composite_backward(raw, d_weights, d_rgb_map, d_acc_map)
+
+
+def composite(eng, raw: torch.Tensor):
+    return _CompositeFn.apply(eng, raw)
+
+
+def render_train(renderer, batch: Dict, epoch: int = -1) -> Dict[str, torch.Tensor]:
+    """``Renderer.render`` with ``net.training`` (inb_renderer.py:53-239): stratified jitter, the network in
+    training mode, compositing, pair and distortion regularisers.  Sampling-distance bookkeeping (linspace, the
+    jitter draw) is the reference's own torch code; everything per sample runs in the CUDA library."""
+    net = renderer.net
+    cfg = net.cfg
+    if epoch != -1:
+        batch["epoch"] = epoch
+    ray_o, ray_d, near, far = batch["ray_o"], batch["ray_d"], batch["near"], batch["far"]
+    n_batch, n_pixel = ray_o.shape[:2]
+    if n_batch != 1:
+        raise ValueError("n_batch must be 1 (the reference asserts it, inb_part_network_multiassign.py:84)")
+    S = cfg.N_samples
+    t_vals = torch.linspace(0.0, 1.0, steps=S, device=near.device, dtype=near.dtype)           # :17
+    z_vals = near[..., None] * (1.0 - t_vals) + far[..., None] * t_vals                         # :18
+    if cfg.perturb > 0.0:                                                                       # :20-27
+        mids = 0.5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], -1)
+        lower = torch.cat([z_vals[..., :1], mids], -1)
+        z_vals = lower + (upper - lower) * torch.rand(z_vals.shape, device=upper.device, dtype=upper.dtype)
+    wpts = ray_o[:, :, None] + ray_d[:, :, None] * z_vals[..., None]                            # :29
+    viewdir = ray_d[:, :, None].expand(-1, -1, S, -1)
+    dists = z_vals[..., 1:] - z_vals[..., :-1]                                                  # :45-47 (unused downstream)
+    dists = torch.cat([dists, dists[..., -1:]], dim=2).reshape(-1)
+    ret = net(wpts.reshape(-1, 3).contiguous(), viewdir.reshape(-1, 3).contiguous(), dists, batch)
+
+    raw = ret["raw"].reshape(n_pixel, S, 4)
+    weights, rgb_map, acc_map = composite(net.engine(), raw)                                    # :72
+    if cfg.use_pair_reg:                                                                        # :78-94
+        tocc = ret["tocc"].view(-1)
+        reg_inds = ((tocc - 0.5).abs() < 0.02).nonzero(as_tuple=True)[0]
+        if reg_inds.numel():
+            reg_tpts = ret["tpts"].view(-1, 3)[reg_inds][None]
+            reg_resd = ret["resd"].view(-1, 3)[reg_inds][None]
+            neighbor = reg_tpts + (torch.rand_like(reg_tpts) - 0.5) * 0.01                     # compute_val_pair_around_range :40
+            ret["oresd"] = torch.cat([reg_resd, net.resd(neighbor, batch)], dim=1)             # :45-46
+        else:
+            ret["oresd"] = torch.zeros(1, 0, 3, device=raw.device)
+    if cfg.use_reg_distortion:                                                                  # :96-103
+        ww = weights.reshape(n_pixel, S, 1) * weights.reshape(n_pixel, 1, S)
+        nxt = torch.cat([z_vals[0, :, 1:], z_vals[0, :, -1:]], dim=-1)
+        mid = (z_vals[0] + nxt) / 2
+        diff = torch.abs(mid.reshape(n_pixel, S, 1) - mid.reshape(n_pixel, 1, S))
+        ret["reg_distortion_loss"] = (ww * diff).sum(dim=-1).sum(dim=-1)[None]
+    ret.update({"rgb_map": rgb_map[None], "acc_map": acc_map[None], "raw": raw.reshape(1, -1, 4)})
+    if cfg.use_freespace_loss:                                                                  # :118-121
+        ret["freespace_occupancy"] = raw[..., 3][batch["occupancy"][0] == 0][None]
+    return ret

@@ -306,14 +306,7 @@ def test_edge_cases(gpu):
     assert torch.isfinite(raw[1:]).all()
 
 
-def test_training_mode_is_loud(gpu):
-    net = gpu["nets"][1.0]
-    net.train()
-    try:
-        with pytest.raises(NotImplementedError):
-            net(torch.zeros(4, 3).cuda(), torch.zeros(4, 3).cuda(), None, gpu["gbatch"])
-    finally:
-        net.eval()
+def test_no_cpu_path(gpu):
     from instant_nvr_b200.network import Network
     cpu_net = Network(gpu["cfg"], device="cpu").eval()
     with pytest.raises(RuntimeError):
