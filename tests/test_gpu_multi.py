@@ -57,3 +57,68 @@ def test_two_rank_nccl_render_equals_single_gpu():
         p.join(300)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _train_worker(rank, world, port, q):
+    """Each rank back-propagates its half of the rays; the all-reduced gradients must equal the single-GPU gradient of
+    the whole batch (the loss is a sum over rays) -- what DDP's gradient all-reduce relies on."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from instant_nvr_b200.config import PathConfig
+    from instant_nvr_b200.network import Network
+    from instant_nvr_b200.renderer import Renderer
+    from instant_nvr_b200.synthetic import fill_weights, make_frame, make_rays
+    cfg = PathConfig.inb_377(N_samples=16, log2_T_cap=12).with_(use_pair_reg=False)
+    frame = make_frame(seed=5)
+    rays = make_rays(frame, 24, 24)
+    net = Network(cfg, device="cpu")
+    fill_weights(net.state_dict(), seed=5, table_gain=100.0, bounds=frame["bounds"][0])
+    net = net.cuda().train()
+    gb = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in {**frame, **rays}.items()}
+    R = gb["ray_o"].shape[1]
+    tgt = torch.rand(1, R, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    r = Renderer(net)
+
+    def grads_for(sel):
+        for p in net.parameters():
+            p.grad = None
+        b = dict(gb)
+        for k in ("ray_o", "ray_d", "near", "far", "occupancy"):
+            b[k] = gb[k][:, sel]
+        ret = r.render(b)
+        (((ret["rgb_map"] - tgt[:, sel]) ** 2).sum() + ret["resd"].pow(2).sum()).backward()
+        return {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in net.named_parameters() if p.requires_grad}
+    full = grads_for(torch.arange(R, device="cuda"))
+    mine = grads_for(torch.arange(rank, R, world, device="cuda"))
+    worst = 0.0
+    for n, g in mine.items():
+        dist.all_reduce(g)
+        worst = max(worst, (g - full[n]).abs().max().item() / (full[n].abs().max().item() + 1e-12))
+    flags = [None] * world
+    dist.all_gather_object(flags, worst)
+    if rank == 0:
+        q.put(max(flags))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_full_batch():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    worst = q.get(timeout=5)
+    print("[multi] worst relative difference of all-reduced gradients:", worst)
+    assert worst < 1e-3
