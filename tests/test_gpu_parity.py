@@ -388,3 +388,40 @@ def test_full_size_properties_c2(full):
     alpha = raw_p.view(-1, S, 4)[..., 3].double()
     acc_ref = 1 - torch.prod(1 - alpha, dim=-1)
     assert (acc_p.double() - acc_ref).abs().max() < 1e-5
+
+
+def test_full_size_properties_c4_c5(full):
+    """BASELINE configs[3] (1024x1024 rays x 64 samples, ray tiles dealt to 8 ranks) and configs[4]
+    (3840x2160 rays x 256 samples = 2.1 G ray-samples, hundreds of passes): size-independent properties."""
+    from instant_nvr_b200.sharding import shard_indices
+    from instant_nvr_b200.synthetic import make_rays
+    cfg, frame, net = full["cfg"], full["frame"], full["net"]
+    eng = net.engine()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    # ---- C4: the union of the 8 interleaved shards reproduces the single-pass frame bit for bit
+    rays = make_rays(frame, 1024, 1024)
+    gb = to_cuda({**frame, **rays})
+    o, d, n, f = gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0]
+    rgb, acc = eng.render_rays(o, d, n, f, 64, batch=gb)
+    assert torch.isfinite(rgb).all() and acc.max() > 0.01
+    out = torch.empty_like(rgb)
+    for r in range(8):
+        idx = shard_indices(1024 * 1024, r, 8).cuda()
+        out[idx] = eng.render_rays(o[idx], d[idx], n[idx], f[idx], 64)[0]
+    assert torch.equal(out, rgb)
+    # ---- C5: 4K x 256 samples
+    rays = make_rays(frame, 2160, 3840)
+    gb = to_cuda({**frame, **rays})
+    o, d, n, f = gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0]
+    torch.cuda.synchronize()
+    t0 = time.time()
+    rgb, acc = eng.render_rays(o, d, n, f, 256, batch=gb)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    diag("c5_render", seconds=dt, ray_samples=2160 * 3840 * 256, g_ray_samples_per_s=2160 * 3840 * 256 / dt / 1e9)
+    assert torch.isfinite(rgb).all() and torch.isfinite(acc).all() and acc.min() >= 0 and acc.max() <= 1 + 1e-5
+    perm = torch.randperm(2160 * 3840, device="cuda", generator=gen)[:4096]
+    rgb_p, acc_p, raw_p = eng.render_rays(o[perm], d[perm], n[perm], f[perm], 256, want_raw=True)
+    assert torch.equal(rgb_p, rgb[perm]) and torch.equal(acc_p, acc[perm])
+    alpha = raw_p.view(-1, 256, 4)[..., 3].double()
+    assert (acc_p.double() - (1 - torch.prod(1 - alpha, dim=-1))).abs().max() < 1e-5
