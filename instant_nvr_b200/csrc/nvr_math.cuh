@@ -47,6 +47,16 @@ NVR_HD float nvr_softplus(float x) {          // torch.nn.Softplus(beta=1, thres
     return x > 20.0f ? x : log1pf(expf(x));
 }
 NVR_HD float nvr_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Softplus of HIDDEN activations on the device: max(x,0) + log1p(exp(-|x|)) on the MUFU units (ex2 / lg2),
+// absolute error ~1e-7 (the next layer only sees it through a dot product), ~5x fewer instructions than the
+// precise form, and equal to x above torch's threshold of 20.  Output heads (occupancy) keep nvr_softplus.
+NVR_HD float nvr_softplus_hidden(float x) {
+#ifdef __CUDA_ARCH__
+    return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x)));
+#else
+    return nvr_softplus(x);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------
 // hash-grid index arithmetic                          part_base_embedder.py:112-136, 158-159
@@ -466,7 +476,7 @@ NVR_HD void nvr_deformer_point(const GridDev& g, const DeformerMlp& m, const Vol
             float acc = m.b0[o];
 #pragma unroll
             for (int i = 0; i < 19; ++i) acc += m.w0[o * 19 + i] * e[i];
-            sc[o * ss] = nvr_softplus(acc);
+            sc[o * ss] = nvr_softplus_hidden(acc);
         }
     }
     {
@@ -478,7 +488,7 @@ NVR_HD void nvr_deformer_point(const GridDev& g, const DeformerMlp& m, const Vol
             float acc = m.b1[o];
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc += m.w1[o * 32 + i] * h1[i];
-            sc[o * ss] = nvr_softplus(acc);
+            sc[o * ss] = nvr_softplus_hidden(acc);
         }
     }
     float acc[3] = {m.b2[0], m.b2[1], m.b2[2]};

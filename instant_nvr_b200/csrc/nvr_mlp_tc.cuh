@@ -232,14 +232,6 @@ __device__ __forceinline__ void gemm3_ss(uint32_t d, uint32_t a_hi_smem, uint32_
     }
 }
 
-// softplus for the HIDDEN activations: max(x,0) + log1p(exp(-|x|)) on the MUFU units (ex2 / lg2), absolute
-// error ~1e-7 -- far inside the 1e-4 per-sample budget and 5x fewer instructions than log1pf(expf(x)).
-// Equals x above torch's threshold of 20 (exp(-20) vanishes against 1).  The occupancy head keeps the
-// precise form.
-__device__ __forceinline__ float softplus_mufu(float x) {
-    const float t = __expf(-fabsf(x));
-    return fmaxf(x, 0.0f) + __logf(1.0f + t);
-}
 // PosEnc (freq_embedder.py:20-31) with one sincosf per axis and double-angle steps for 2v, 4v, 8v
 // (absolute error < 1e-6, against 24 separate sinf / cosf calls).
 __device__ __forceinline__ void posenc27_doubling(const float v[3], float* out) {
@@ -343,7 +335,7 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
             tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                h[k] = softplus_mufu(h[k] + b0[c * 16 + k]);        // MLP.forward :20-22
+                h[k] = nvr_softplus_hidden(h[k] + b0[c * 16 + k]);        // MLP.forward :20-22
                 o0 += w1[c * 16 + k] * h[k];
             }
             tmem_st16_split(trow + TC_COL_HHI + c * 16, trow + TC_COL_HLO + c * 16, h);
@@ -369,7 +361,7 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
                 tmem_ld16(trow + TC_COL_D + c * 16, g);
                 tmem_wait_ld();
 #pragma unroll
-                for (int k = 0; k < 16; ++k) g[k] = softplus_mufu(g[k] + b2[c * 16 + k]);
+                for (int k = 0; k < 16; ++k) g[k] = nvr_softplus_hidden(g[k] + b2[c * 16 + k]);
                 tmem_st16_split(trow + TC_COL_HHI + c * 16, trow + TC_COL_HLO + c * 16, g);
             }
             tmem_wait_st();
@@ -393,7 +385,7 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
             tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const float a = softplus_mufu(g[k] + bl[c * 16 + k]);
+                const float a = nvr_softplus_hidden(g[k] + bl[c * 16 + k]);
                 r[0] += w4[c * 16 + k] * a; r[1] += w4[64 + c * 16 + k] * a; r[2] += w4[128 + c * 16 + k] * a;
             }
         }

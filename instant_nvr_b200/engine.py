@@ -70,7 +70,7 @@ def _params_struct(net, grads: Optional[Dict[str, torch.Tensor]] = None) -> "cab
 
 
 class Engine:
-    def __init__(self, cfg: PathConfig, device: Optional[torch.device] = None, max_points_per_pass: int = 8 << 20,
+    def __init__(self, cfg: PathConfig, device: Optional[torch.device] = None, max_points_per_pass: int = 32 << 20,
                  mlp_mode: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("instant_nvr_b200 needs a CUDA device: the hot path has no CPU implementation")
@@ -81,7 +81,7 @@ class Engine:
         self.cfg = cfg
         self.lib = cabi.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.max_points_per_pass = int(max_points_per_pass)
+        self.max_points_per_pass = int(os.environ.get("NVR_PASS_POINTS", max_points_per_pass))
         conf = cabi.NvrConfig(cabi.ABI_VERSION, self.device.index or 0, float(cfg.smpl_thresh), int(mlp_mode))
         h = C.c_void_p()
         rc = self.lib.nvr_create(C.byref(conf), C.byref(h))
