@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 4
+#define NVR_ABI_VERSION 5
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -179,6 +179,15 @@ int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const float* dirs,
  * All n points must fit one pass. */
 int nvr_query_points_debug(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw,
                            int32_t* surv_of_sample, float* warp_dbg, void* workspace, size_t ws_bytes, void* stream);
+
+/* Inference tables (opt-in).  The part networks consume only the per-level SUM of an entry's 16 features
+ * (part_base_embedder.py:165), so for forward-only rendering the sums can be taken once per weight update:
+ * nvr_prepare_inference(h, 1, stream) builds (dense rows + hash rows) fp32 sums per part (286 MB for inb_377) and
+ * makes nvr_query_points / nvr_render_rays* gather 4 B per corner instead of 64 B.  Results differ from the full
+ * tables only by fp32 re-association (sum_c w_c sum_f t vs sum_f sum_c w_c t).  The sums are a SNAPSHOT: call
+ * again after the tables changed; nvr_bind_params and nvr_prepare_inference(h, 0, ...) drop them.  Training entry
+ * points always read the full tables. */
+int nvr_prepare_inference(NvrHandle h, int32_t enable, void* stream);
 
 /* ==================== training ====================
  * Network.forward in training mode (inb_part_network_multiassign.py:126-168 with self.training) and its

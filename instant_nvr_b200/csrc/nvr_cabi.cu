@@ -35,6 +35,9 @@ struct NvrEngine {
     long long perm_key = 0; int perm_maxlen = 0;           // topology the partition was built for
     PartMlpDev* d_part_mlp = nullptr;       // device copy of part_mlp[] for k_mlp_prep
     float* d_mlp_blocks = nullptr;          // NVR_PARTS packed tcgen05 parameter blocks (mlp_mode 1)
+    float* d_presum = nullptr; size_t presum_cap = 0;     // inference tables: per part [dense rows | hash rows] sums
+    size_t presum_off[NVR_PARTS + 1] = {0};
+    bool presum_valid = false;
     int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
     long long launches = 0;
     long long last_points = 0;
@@ -135,7 +138,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
 extern "C" int nvr_destroy(NvrHandle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_perm); cudaFree(h->d_part_mlp); cudaFree(h->d_mlp_blocks); cudaFree(h->d_counters_snapshot);
+    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_perm); cudaFree(h->d_part_mlp); cudaFree(h->d_mlp_blocks); cudaFree(h->d_presum); cudaFree(h->d_counters_snapshot);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
     delete h;
@@ -185,6 +188,7 @@ extern "C" int nvr_bind_params(NvrHandle h, const NvrParams* p) {
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
     NVR_CHECK(h, cudaMemcpy(h->d_part_mlp, h->part_mlp, sizeof(h->part_mlp), cudaMemcpyHostToDevice));
     h->have_params = true;
+    h->presum_valid = false;                 // new storages: the inference tables must be rebuilt
     return 0;
 }
 
@@ -277,6 +281,13 @@ static bool carve(void* ws, size_t bytes, Workspace& w) {
     return true;
 }
 
+static long long dense_rows(const NvrGrid& g) {
+    long long r = 0;
+    for (int l = 0; l < g.start_hash && l < g.n_levels; ++l) r += (long long)g.res[l] * g.res[l] * g.res[l];
+    return r;
+}
+static long long hash_rows(const NvrGrid& g) { return (long long)(g.n_levels - g.start_hash) * g.table_size; }
+
 static int grid_for(long long items, int per_block, int max_blocks) {
     long long b = (items + per_block - 1) / per_block;
     return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
@@ -285,7 +296,7 @@ static int grid_for(long long items, int per_block, int max_blocks) {
 // One pass over `n` samples (n <= ws.cap): cull -> warp -> 5x(embed, mlp).  The caller resolves.
 static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const float* ray_d, const float* near_,
                     const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
-                    float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr) {
+                    float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr, bool full_tables = false) {
     const int sm = h->sm_count;
     NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
     { StageTimer t(h, st, NVR_STAGE_CULL);
@@ -308,8 +319,14 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
         { StageTimer t(h, st, NVR_STAGE_EMBED);
-        k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
-                                                         el, NVR_EMB_STRIDE); }
+        if (h->presum_valid && !full_tables) {
+            const float* sd = h->d_presum + h->presum_off[p];
+            k_embed_presum<<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->part_grid[p], sd, sd + dense_rows(h->params.part[p].grid), (const float*)pl, 8,
+                                                                    w.counters + NVR_CTR_PAIR + p, 0, el, NVR_EMB_STRIDE);
+        } else {
+            k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
+                                                             el, NVR_EMB_STRIDE);
+        } }
         StageTimer t(h, st, NVR_STAGE_MLP);
         if (tc)
             k_mlp_tc<<<grid_for(n, 256, sm), TC_THREADS, TC_SMEM_BYTES, st>>>(h->d_mlp_blocks + (size_t)p * TC_BLOCK_FLOATS, h->part_mlp[p].n_rgb, p,
@@ -477,6 +494,37 @@ extern "C" int nvr_query_points_debug(NvrHandle h, const float* wpts, const floa
     return snapshot_counters(h, w, st);
 }
 
+// ---- inference tables ----------------------------------------------------------------------------
+extern "C" int nvr_prepare_inference(NvrHandle h, int32_t enable, void* stream_) {
+    if (!h || !h->have_params) return fail(h, "nvr_prepare_inference: bind_params first");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    if (!enable) { h->presum_valid = false; return 0; }
+    size_t total = 0;
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) {
+        h->presum_off[p] = total;
+        total += (size_t)(dense_rows(h->params.part[p].grid) + hash_rows(h->params.part[p].grid));
+    }
+    h->presum_off[NVR_NUM_PARTS] = total;
+    if (total > h->presum_cap) {
+        NVR_CHECK(h, cudaFree(h->d_presum));
+        h->d_presum = nullptr; h->presum_cap = 0;
+        NVR_CHECK(h, cudaMalloc(&h->d_presum, total * sizeof(float)));
+        h->presum_cap = total;
+    }
+    cudaStream_t st = (cudaStream_t)stream_;
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) {
+        const NvrGrid& g = h->params.part[p].grid;
+        const long long nd = dense_rows(g), nh = hash_rows(g);
+        float* out = h->d_presum + h->presum_off[p];
+        k_presum_rows<<<grid_for(nd, 256, h->sm_count * 16), 256, 0, st>>>(g.dense, nd, out);
+        k_presum_rows<<<grid_for(nh, 256, h->sm_count * 16), 256, 0, st>>>(g.hash, nh, out + nd);
+    }
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches += 2 * NVR_NUM_PARTS;
+    h->presum_valid = true;
+    return 0;
+}
+
 // ---- training ----------------------------------------------------------------------------------
 __global__ void k_export_slots(const int* __restrict__ counters, const float4* __restrict__ surv, const float4* __restrict__ raws,
                                float* __restrict__ tocc, int* __restrict__ sample_of_slot) {
@@ -501,7 +549,7 @@ extern "C" int nvr_train_forward(NvrHandle h, const float* wpts, const float* vi
     NVR_CHECK(h, cudaMemsetAsync(x0, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
     NVR_CHECK(h, cudaMemsetAsync(resd, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
     NVR_CHECK(h, cudaMemsetAsync(tocc, 0, (size_t)n * NVR_NUM_PARTS * sizeof(float), st));
-    if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, nullptr, x0, resd)) return rc;
+    if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, nullptr, x0, resd, true)) return rc;
     k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, n, (float4*)raw, occ);
     k_export_slots<<<grid_for(n, 256, h->sm_count * 8), 256, 0, st>>>(w.counters, w.surv, w.raws, tocc, sample_of_slot);
     NVR_CHECK(h, cudaGetLastError());

@@ -584,6 +584,75 @@ k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restr
 }
 
 // -----------------------------------------------------------------------------------------
+// inference tables: the part networks only ever consume sum_f of an entry (part_base_embedder.py:165), so for
+// forward-only rendering the 16 features of every row can be summed ONCE per weight update: 4 B per corner
+// instead of 64 B (16x less gather traffic; SURVEY.md section 7 "legal algorithmic win").  Opt-in
+// (nvr_prepare_inference); training and the roofline-defined run use the full tables.
+// -----------------------------------------------------------------------------------------
+__global__ void k_presum_rows(const float* __restrict__ tab, long long n_rows, float* __restrict__ out) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        const float4* t4 = reinterpret_cast<const float4*>(tab + r * 16);
+        const float4 a = __ldg(t4), b = __ldg(t4 + 1), c = __ldg(t4 + 2), d = __ldg(t4 + 3);
+        out[r] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) + (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+    }
+}
+
+// Same contract as k_embed, on the pre-summed tables (sd = dense sums, sh = hash sums): one lane = one point.
+__global__ void __launch_bounds__(256)
+k_embed_presum(GridDev g, const float* __restrict__ sd, const float* __restrict__ sh, const float* __restrict__ xb, int xstride,
+               const int* __restrict__ count_dev, int n_imm, float* __restrict__ eb, int emb_stride) {
+    const int n = count_dev ? *count_dev : n_imm;
+    const bool fast_mod = g.T_magic40 != 0;
+    const unsigned int T32 = (unsigned int)g.T;
+    for (int pt = blockIdx.x * blockDim.x + threadIdx.x; pt < n; pt += gridDim.x * blockDim.x) {
+        const float* xp = xb + (long long)pt * xstride;
+        const float x[3] = {xp[0], xp[1], xp[2]};
+        float u[3];
+        nvr_normalise(g, x, u);
+        float* o = eb + (long long)pt * emb_stride;
+        o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+#pragma unroll 1
+        for (int l = 0; l < g.n_levels; ++l) {
+            const int res = g.res[l];
+            int i0[3], i1[3];
+            float of[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) axis_coord(u[a], g.size[l], res, i0[a], i1[a], of[a]);
+            unsigned int row[8];
+            const float* tab;
+            if (l < g.start_hash) {
+                tab = sd;
+                const unsigned int off = (unsigned int)g.dense_off[l];
+                const unsigned int ax[2] = {(unsigned int)(i0[0] * res * res) + off, (unsigned int)(i1[0] * res * res) + off};
+                const unsigned int ay[2] = {(unsigned int)(i0[1] * res), (unsigned int)(i1[1] * res)};
+                const unsigned int az[2] = {(unsigned int)i0[2], (unsigned int)i1[2]};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) row[c] = ax[(c >> 2) & 1] + ay[(c >> 1) & 1] + az[c & 1];
+            } else {
+                tab = sh;
+                const unsigned int off = (unsigned int)(l - g.start_hash) * T32;
+                const unsigned long long hx[2] = {(unsigned long long)i0[0], (unsigned long long)i1[0]};
+                const unsigned long long hy[2] = {(unsigned long long)i0[1] * 19349663ull, (unsigned long long)i1[1] * 19349663ull};
+                const unsigned long long hz[2] = {(unsigned long long)i0[2] * 83492791ull, (unsigned long long)i1[2] * 83492791ull};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const unsigned long long h = hx[(c >> 2) & 1] ^ hy[(c >> 1) & 1] ^ hz[c & 1];
+                    row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
+                }
+            }
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + row[c]);
+            const float wx[2] = {1.0f - of[0], of[0]}, wy[2] = {1.0f - of[1], of[1]}, wz[2] = {1.0f - of[2], of[2]};
+            float lev = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) lev += ((wx[(c >> 2) & 1] * wy[(c >> 1) & 1]) * wz[c & 1]) * v[c];
+            o[3 + l] = lev;
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------
 // occ + rgb MLPs, fp32 register tiles                      part_base_network.py:44-63
 // -----------------------------------------------------------------------------------------
 #define MLP_TILE 128

@@ -71,13 +71,16 @@ def _params_struct(net, grads: Optional[Dict[str, torch.Tensor]] = None) -> "cab
 
 class Engine:
     def __init__(self, cfg: PathConfig, device: Optional[torch.device] = None, max_points_per_pass: int = 32 << 20,
-                 mlp_mode: Optional[int] = None):
+                 mlp_mode: Optional[int] = None, inference_tables: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("instant_nvr_b200 needs a CUDA device: the hot path has no CPU implementation")
         cfg.check_supported()
         if mlp_mode is None:        # 1: tcgen05 3xTF32 tensor-core tiles (default); 0: fp32 FFMA tiles
             mlp_mode = int(os.environ.get("NVR_MLP_MODE", DEFAULT_MLP_MODE))
         self.mlp_mode = int(mlp_mode)
+        # pre-summed inference tables (nvr_prepare_inference): opt-in, NVR_INFERENCE_TABLES=1 or the constructor flag
+        self.inference_tables = bool(int(os.environ.get("NVR_INFERENCE_TABLES", "0"))) if inference_tables is None else bool(inference_tables)
+        self._tables_key = None
         self.cfg = cfg
         self.lib = cabi.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -115,6 +118,15 @@ class Engine:
     def invalidate_params(self) -> None:
         self._params_key = None
 
+    def _refresh_inference_tables(self) -> None:
+        """Re-sum the tables when they changed in place (optimizer steps bump ``_version``); eval entry points only."""
+        if not self.inference_tables:
+            return
+        key = tuple((t.data_ptr(), t._version) for t in self._net_tables)
+        if key != self._tables_key:
+            self._check(self.lib.nvr_prepare_inference(self._h, 1, _stream_ptr()), "nvr_prepare_inference")
+            self._tables_key = key
+
     def bind_params(self, net) -> None:
         """``net``: instant_nvr_b200.network.Network (or any module with the same tree)."""
         tensors = [p for p in net.parameters()]
@@ -130,6 +142,8 @@ class Engine:
         P = _params_struct(net)
         self._check(self.lib.nvr_bind_params(self._h, C.byref(P)), "nvr_bind_params")
         self._params_key, self._params_keep = key, tensors
+        self._tables_key = None
+        self._net_tables = [t for part in net.tpose_human.part_networks for t in (part.embedder.dense, part.embedder.hash)]
 
     # ---- frame --------------------------------------------------------------------------------
     def bind_frame(self, batch: Dict, force: bool = False) -> None:
@@ -190,6 +204,7 @@ class Engine:
     def query_points(self, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict):
         """Network.forward (eval): (N,3),(N,3) -> raw (N,4), occ (N,1) on the device."""
         self.bind_frame(batch)
+        self._refresh_inference_tables()
         wpts, viewdir = _dev_f32(wpts, self.device), _dev_f32(viewdir, self.device)
         n = wpts.shape[0]
         raw = torch.empty(n, 4, dtype=torch.float32, device=self.device)
@@ -203,6 +218,7 @@ class Engine:
         """Renderer.render (eval): rays (R,3),(R,3),(R,),(R,) -> rgb_map (R,3), acc_map (R,) [, raw (R*S,4)]."""
         if batch is not None:
             self.bind_frame(batch)
+        self._refresh_inference_tables()
         ray_o, ray_d = _dev_f32(ray_o, self.device), _dev_f32(ray_d, self.device)
         near, far = _dev_f32(near, self.device), _dev_f32(far, self.device)
         R = ray_o.shape[0]
@@ -218,6 +234,7 @@ class Engine:
 
     def render_rays_host(self, ray_o, ray_d, near, far, n_samples: int, rgb_out, acc_out) -> None:
         """Host (pinned) ray buffers in, host rgb_map / acc_map out; copies are part of the call."""
+        self._refresh_inference_tables()
         for t in (ray_o, ray_d, near, far, rgb_out, acc_out):
             if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("render_rays_host takes contiguous fp32 CPU tensors")

@@ -425,3 +425,30 @@ def test_full_size_properties_c4_c5(full):
     assert torch.equal(rgb_p, rgb[perm]) and torch.equal(acc_p, acc[perm])
     alpha = raw_p.view(-1, 256, 4)[..., 3].double()
     assert (acc_p.double() - (1 - torch.prod(1 - alpha, dim=-1))).abs().max() < 1e-5
+
+
+def test_inference_tables_match_full_tables(gpu):
+    """Opt-in pre-summed inference tables: same render within fp32 re-association, and they follow in-place updates."""
+    from instant_nvr_b200.engine import Engine
+    cfg, net, gb = gpu["cfg"], gpu["nets"][200.0], gpu["gbatch"]
+    eng_full = Engine(cfg, inference_tables=False)
+    eng_full.bind_params(net)
+    eng_sum = Engine(cfg, inference_tables=True)
+    eng_sum.bind_params(net)
+    o, d, n, f = gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0]
+    rgb_a, acc_a, raw_a = eng_full.render_rays(o, d, n, f, cfg.N_samples, batch=gb, want_raw=True)
+    rgb_b, acc_b, raw_b = eng_sum.render_rays(o, d, n, f, cfg.N_samples, batch=gb, want_raw=True)
+    err = (raw_a - raw_b).abs().max().item()
+    diag("inference_tables", max_raw_diff=err, psnr=O.psnr(rgb_b.cpu(), rgb_a.cpu()))
+    assert err < 2e-4 and O.psnr(rgb_b.cpu(), rgb_a.cpu()) > 80
+    # an in-place weight update must be picked up (the sums are a snapshot keyed on tensor versions)
+    tab = net.tpose_human.part_networks[0].embedder.dense
+    with torch.no_grad():
+        tab.mul_(0.5)
+    try:
+        rgb_c = eng_sum.render_rays(o, d, n, f, cfg.N_samples, batch=gb)[0]
+        rgb_d = eng_full.render_rays(o, d, n, f, cfg.N_samples, batch=gb)[0]
+        assert (rgb_c - rgb_d).abs().max() < 1e-4 and (rgb_c - rgb_b).abs().max() > 1e-4
+    finally:
+        with torch.no_grad():
+            tab.mul_(2.0)
