@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 5
+#define NVR_ABI_VERSION 6
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -227,6 +227,47 @@ int nvr_composite_forward(NvrHandle h, const float* raw, int64_t n_rays, int32_t
                           float* rgb_map, float* acc_map, void* stream);
 int nvr_composite_backward(NvrHandle h, const float* raw, int64_t n_rays, int32_t n_samples, const float* d_weights,
                            const float* d_rgb_map, const float* d_acc_map, float* d_raw, void* stream);
+
+/* ==================== the steps either side of the path ====================
+ *
+ * -- Optimizer step (8(f) rank 1).  torch.optim.Adam as lib/train/optimizer.py:13-31 builds it (one param group
+ * per tensor, amsgrad off, eps = cfg.train.eps = 1e-15), applied to every listed tensor in ONE pass over HBM:
+ * 28 B per element (read p, g, m, v; write p, m, v) against the ~70 B of the library's multi-kernel foreach form.
+ * `tensors` is a HOST array; every pointer in it is a device pointer to `numel` contiguous fp32 values.
+ * `step` is the 1-based number of THIS update of that tensor (torch keeps one counter per parameter).  The bias
+ * corrections are taken in double on the host exactly as torch does (1 - beta**step).  zero_grad != 0 also clears
+ * the gradient buffers in the same pass (optimizer.zero_grad(set_to_none=False) for free). */
+typedef struct NvrAdamTensor {
+    float* param;
+    float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t numel;
+    int64_t step;
+    double lr;
+    double weight_decay;
+} NvrAdamTensor;
+int nvr_adam_step(NvrHandle h, const NvrAdamTensor* tensors, int32_t n_tensors, double beta1, double beta2, double eps,
+                  int32_t zero_grad, void* stream);
+
+/* -- Camera rays (8(f) rank 2): get_rays + get_near_far + the mask_at_box compaction, i.e.
+ * get_rays_within_bounds / get_rays_within_bounds_coord (lib/utils/if_nerf/if_nerf_data_utils.py:24-38, 92-107,
+ * 329-362), which the reference runs in numpy on DataLoader workers for every frame (tpose_dataset.py:438,
+ * tpose_novel_view_dataset.py:206).  Host inputs: K_inv = inv(K) (3,3), R (3,3), T (3) row-major doubles (the
+ * reference's get_rays works in float64).  `bounds` (2,3) fp32 is a DEVICE pointer (world-space bbox).
+ * Outputs (device, capacity H*W rays): ray_o, ray_d (n,3), near, far (n), coord (n) int32 = pixel index row*W + col of
+ * each surviving ray in row-major order (may be NULL), mask_at_box (H*W) uint8, n_rays (1) int32.
+ * `workspace` needs nvr_rays_workspace_bytes(H, W) bytes. */
+size_t nvr_rays_workspace_bytes(int32_t H, int32_t W);
+int nvr_generate_rays(NvrHandle h, int32_t H, int32_t W, const double* K_inv_host, const double* R_host, const double* T_host,
+                      const float* bounds, float* ray_o, float* ray_d, float* near_, float* far_, int32_t* coord,
+                      uint8_t* mask_at_box, int32_t* n_rays, void* workspace, size_t ws_bytes, void* stream);
+
+/* -- Image assembly and the evaluator's MSE (8(f) rank 4; lib/evaluators/if_nerf.py:28-31, 84-113):
+ * img (n_pixels,3) = 0, img[coord[r]] = rgb[r];   sq_sum[0] = sum_i ((double)a[i] - (double)b[i])^2  (the caller divides
+ * by n and takes -10 log10 for the PSNR).  sq_sum is a device double, overwritten. */
+int nvr_assemble_image(NvrHandle h, const float* rgb, const int32_t* coord, int64_t n_rays, int64_t n_pixels, float* img, void* stream);
+int nvr_sq_diff_sum(NvrHandle h, const float* a, const float* b, int64_t n, double* sq_sum, void* stream);
 
 /* Per-stage device timing.  nvr_profile(h, 1) clears the accumulators and makes every later launch
  * record a CUDA-event pair on its stream; nvr_profile_read synchronises the device and sums them. */

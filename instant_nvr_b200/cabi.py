@@ -12,7 +12,7 @@ from typing import Optional
 
 MAX_LEVELS = 16
 NUM_PARTS = 5
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnvr_b200.so")
@@ -71,6 +71,11 @@ class NvrStageProfile(C.Structure):
                 ("pairs", C.c_int64 * NUM_PARTS)]
 
 
+class NvrAdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("step", C.c_int64), ("lr", C.c_double), ("weight_decay", C.c_double)]
+
+
 STAGE_NAMES = ("prep", "cull", "knn", "warp", "embed", "mlp", "resolve")
 
 # name -> (restype, argtypes); exactly the declarations of include/nvr_b200.h
@@ -104,6 +109,14 @@ SYMBOLS = {
     "nvr_composite_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nvr_composite_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
+    "nvr_adam_step": (C.c_int, [C.c_void_p, C.POINTER(NvrAdamTensor), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                C.c_void_p]),
+    "nvr_rays_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "nvr_generate_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nvr_assemble_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nvr_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nvr_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "nvr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(NvrStageProfile)]),
     "nvr_read_counters": (C.c_int, [C.c_void_p, C.POINTER(NvrCounters), C.c_void_p]),

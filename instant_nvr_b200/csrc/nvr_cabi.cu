@@ -3,6 +3,7 @@
 // Host-side orchestration only: pointer bookkeeping, pass splitting, launches.  There is no CPU
 // compute path here; every entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -14,6 +15,7 @@
 #include "nvr_kernels.cuh"
 #include "nvr_mlp_tc.cuh"
 #include "nvr_train.cuh"
+#include "nvr_aux.cuh"
 
 struct NvrEngine {
     NvrConfig cfg;
@@ -653,6 +655,110 @@ extern "C" int nvr_composite_backward(NvrHandle h, const float* raw, int64_t n_r
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
     k_composite_bwd<<<grid_for(n_rays, 128, h->sm_count * 8), 128, 0, (cudaStream_t)stream_>>>((const float4*)raw, n_rays, n_samples, d_weights,
                                                                                              d_rgb_map, d_acc_map, (float4*)d_raw);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// ---- optimizer step / camera rays / image metrics --------------------------------
+extern "C" int nvr_adam_step(NvrHandle h, const NvrAdamTensor* tensors, int32_t n_tensors, double beta1, double beta2, double eps,
+                             int32_t zero_grad, void* stream_) {
+    if (!h) return 1;
+    if (n_tensors < 0 || (n_tensors > 0 && !tensors)) return fail(h, "nvr_adam_step: null argument");
+    if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0)) return fail(h, "nvr_adam_step: bad betas / eps");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream_;
+    AdamBatch b;
+    memset(&b, 0, sizeof(b));
+    b.zero_grad = zero_grad != 0;
+    auto flush = [&]() -> cudaError_t {
+        if (b.n_tensors == 0) return cudaSuccess;
+        k_adam<<<b.chunk_begin[b.n_tensors], 256, 0, st>>>(b);
+        h->launches++;
+        b.n_tensors = 0;
+        return cudaGetLastError();
+    };
+    for (int i = 0; i < n_tensors; ++i) {
+        const NvrAdamTensor& t = tensors[i];
+        if (t.numel == 0) continue;
+        if (t.numel < 0 || !t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq || t.step < 1)
+            return fail(h, "nvr_adam_step: tensor with null pointer, negative numel or step < 1");
+        const long long chunks = (t.numel + ADAM_CHUNK - 1) / ADAM_CHUNK;
+        if (chunks >= (1ll << 30)) return fail(h, "nvr_adam_step: tensor too large");
+        if (b.n_tensors == ADAM_MAX_TENSORS || (long long)b.chunk_begin[b.n_tensors] + chunks >= (1ll << 31)) NVR_CHECK(h, flush());
+        AdamTensorDev& d = b.t[b.n_tensors];
+        d.p = t.param; d.g = t.grad; d.m = t.exp_avg; d.v = t.exp_avg_sq; d.n = t.numel;
+        d.vec = (((uintptr_t)t.param | (uintptr_t)t.grad | (uintptr_t)t.exp_avg | (uintptr_t)t.exp_avg_sq) & 15) == 0;
+        const double bc1 = 1.0 - pow(beta1, (double)t.step), bc2 = 1.0 - pow(beta2, (double)t.step);
+        d.s.beta1 = (float)beta1; d.s.beta2 = (float)beta2;
+        d.s.one_minus_beta1 = (float)(1.0 - beta1); d.s.one_minus_beta2 = (float)(1.0 - beta2);
+        d.s.eps = (float)eps; d.s.weight_decay = (float)t.weight_decay;
+        d.s.neg_step_size = (float)(-(t.lr / bc1));
+        d.s.bc2_sqrt = (float)sqrt(bc2);
+        if (b.n_tensors == 0) b.chunk_begin[0] = 0;
+        b.chunk_begin[b.n_tensors + 1] = b.chunk_begin[b.n_tensors] + (int)chunks;
+        b.n_tensors++;
+    }
+    NVR_CHECK(h, flush());
+    return 0;
+}
+
+extern "C" size_t nvr_rays_workspace_bytes(int32_t H, int32_t W) {
+    const long long tiles = ((long long)(H > 0 ? H : 0) * (W > 0 ? W : 0) + RAYS_BLOCK - 1) / RAYS_BLOCK;
+    return (size_t)(2 * tiles + 2) * sizeof(int);
+}
+
+extern "C" int nvr_generate_rays(NvrHandle h, int32_t H, int32_t W, const double* K_inv, const double* R, const double* T,
+                                 const float* bounds, float* ray_o, float* ray_d, float* near_, float* far_, int32_t* coord,
+                                 uint8_t* mask_at_box, int32_t* n_rays, void* workspace, size_t ws_bytes, void* stream_) {
+    if (!h) return 1;
+    if (H < 1 || W < 1 || (long long)H * W >= (1ll << 31)) return fail(h, "nvr_generate_rays: bad image size");
+    if (!K_inv || !R || !T || !bounds || !ray_o || !ray_d || !near_ || !far_ || !mask_at_box || !n_rays)
+        return fail(h, "nvr_generate_rays: null argument");
+    if (!workspace || ws_bytes < nvr_rays_workspace_bytes(H, W) || ((uintptr_t)workspace & 3))
+        return fail(h, "nvr_generate_rays: workspace too small (nvr_rays_workspace_bytes)");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    CameraDev cam;
+    for (int i = 0; i < 9; ++i) { cam.Kinv[i] = K_inv[i]; cam.R[i] = R[i]; }
+    for (int a = 0; a < 3; ++a) {
+        cam.T[a] = T[a];
+        cam.o[a] = -((R[0 * 3 + a] * T[0] + R[1 * 3 + a] * T[1]) + R[2 * 3 + a] * T[2]);     // -R^T T (:26)
+    }
+    const int tiles = (int)(((long long)H * W + RAYS_BLOCK - 1) / RAYS_BLOCK);
+    int* tile_count = (int*)workspace;
+    int* tile_off = tile_count + tiles;
+    cudaStream_t st = (cudaStream_t)stream_;
+    k_rays_mask<<<tiles, RAYS_BLOCK, 0, st>>>(cam, H, W, bounds, mask_at_box, tile_count);
+    k_rays_scan<<<1, 1024, 0, st>>>(tile_count, tiles, tile_off, n_rays);
+    k_rays_emit<<<tiles, RAYS_BLOCK, 0, st>>>(cam, H, W, bounds, tile_off, ray_o, ray_d, near_, far_, coord);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches += 3;
+    return 0;
+}
+
+extern "C" int nvr_assemble_image(NvrHandle h, const float* rgb, const int32_t* coord, int64_t n_rays, int64_t n_pixels, float* img,
+                                  void* stream_) {
+    if (!h) return 1;
+    if (n_rays < 0 || n_pixels < 0 || n_rays > n_pixels || (n_pixels > 0 && !img) || (n_rays > 0 && (!rgb || !coord)))
+        return fail(h, "nvr_assemble_image: bad argument");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream_;
+    NVR_CHECK(h, cudaMemsetAsync(img, 0, (size_t)n_pixels * 3 * sizeof(float), st));
+    if (n_rays == 0) return 0;
+    k_assemble_image<<<grid_for(n_rays, 256, h->sm_count * 8), 256, 0, st>>>(rgb, coord, n_rays, img);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" int nvr_sq_diff_sum(NvrHandle h, const float* a, const float* b, int64_t n, double* sq_sum, void* stream_) {
+    if (!h) return 1;
+    if (n < 0 || !sq_sum || (n > 0 && (!a || !b))) return fail(h, "nvr_sq_diff_sum: bad argument");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream_;
+    NVR_CHECK(h, cudaMemsetAsync(sq_sum, 0, sizeof(double), st));
+    if (n == 0) return 0;
+    k_sq_diff<<<grid_for(n, 256 * 8, h->sm_count * 8), 256, 0, st>>>(a, b, n, sq_sum);
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return 0;

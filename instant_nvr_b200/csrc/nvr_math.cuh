@@ -530,3 +530,80 @@ NVR_HD void nvr_dir_to_pose(const float* R, const float d[3], float v[3]) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = (d[0] * R[0 * 3 + c] + d[1] * R[1 * 3 + c]) + d[2] * R[2 * 3 + c];
 }
+
+// ---------------------------------------------------------------------------------------
+// camera rays, the step before the path        lib/utils/if_nerf/if_nerf_data_utils.py:24-38 (get_rays),
+//                                               :92-107 (get_near_far), :329-343 (get_rays_within_bounds)
+// ---------------------------------------------------------------------------------------
+// get_rays runs in float64 in the reference (K, R, T come from the annotation files as float64; only the
+// result is cast to float32, :332-333), so the pixel -> ray arithmetic here is double as well.
+struct CameraDev {
+    double Kinv[9];                // np.linalg.inv(K), row-major (taken on the host with the same LAPACK call)
+    double R[9];                   // world -> camera rotation, row-major
+    double T[3];
+    double o[3];                   // camera origin -R^T T (:26)
+};
+
+// pixel (col i, row j) -> unit ray direction (float32, as after `.astype(np.float32)`)
+NVR_HD void nvr_pixel_ray(const CameraDev& c, int i, int j, float ray_d[3]) {
+    const double xy1[3] = {(double)(float)i, (double)(float)j, 1.0};
+    double pc[3], pw[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)                                  // xy1 . inv(K)^T  (:32)
+        pc[a] = (xy1[0] * c.Kinv[a * 3 + 0] + xy1[1] * c.Kinv[a * 3 + 1]) + xy1[2] * c.Kinv[a * 3 + 2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)                                  // (pixel_camera - T) . R  (:33)
+        pw[a] = ((pc[0] - c.T[0]) * c.R[0 * 3 + a] + (pc[1] - c.T[1]) * c.R[1 * 3 + a]) + (pc[2] - c.T[2]) * c.R[2 * 3 + a];
+    const double d[3] = {pw[0] - c.o[0], pw[1] - c.o[1], pw[2] - c.o[2]};   // :35
+    const double nrm = sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);     // :36
+#pragma unroll
+    for (int a = 0; a < 3; ++a) ray_d[a] = (float)(d[a] / nrm);
+}
+
+#ifdef __CUDA_ARCH__
+#define NVR_FMUL(a, b) __fmul_rn((a), (b))
+#define NVR_FADD(a, b) __fadd_rn((a), (b))
+#else
+#define NVR_FMUL(a, b) ((a) * (b))
+#define NVR_FADD(a, b) ((a) + (b))
+#endif
+
+// get_near_far (:92-107) in float32 on one ray; `o0` is the FIRST ray's origin (the reference indexes
+// ray_o[:1], i.e. it assumes one camera origin for the whole batch).  Returns mask_at_box = near < far;
+// near / far are already divided by |ray_d| (:105-106).  No fused multiply-adds: near < far is a bit-level
+// decision in the reference.
+NVR_HD bool nvr_near_far(const float* bounds /* (2,3) */, const float o0[3], const float ray_d[3], float* near_, float* far_) {
+    const float norm_d = sqrtf(NVR_FADD(NVR_FADD(NVR_FMUL(ray_d[0], ray_d[0]), NVR_FMUL(ray_d[1], ray_d[1])), NVR_FMUL(ray_d[2], ray_d[2])));
+    float nr = -INFINITY, fr = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float v = ray_d[a] / norm_d;
+        if (v < 1e-5f && v > -1e-10f) v = 1e-5f;                 // :96
+        if (v > -1e-5f && v < 1e-10f) v = -1e-5f;                // :97
+        const float tmin = (bounds[a] - o0[a]) / v;              // :98
+        const float tmax = (bounds[3 + a] - o0[a]) / v;          // :99
+        nr = fmaxf(nr, fminf(tmin, tmax));                       // :100,102
+        fr = fminf(fr, fmaxf(tmin, tmax));                       // :101,103
+    }
+    *near_ = nr / norm_d;
+    *far_ = fr / norm_d;
+    return nr < fr;                                              // :104
+}
+
+// ---------------------------------------------------------------------------------------
+// Adam, one element                torch.optim.Adam (single-tensor form, amsgrad=False, maximize=False) as
+//                                  lib/train/optimizer.py:27 constructs it (eps = cfg.train.eps = 1e-15)
+// ---------------------------------------------------------------------------------------
+struct AdamScalars {
+    float beta1, beta2, one_minus_beta1, one_minus_beta2;
+    float eps, weight_decay;
+    float neg_step_size;           // -lr / (1 - beta1^t)
+    float bc2_sqrt;                // sqrt(1 - beta2^t)
+};
+NVR_HD void nvr_adam_update(const AdamScalars& s, float& p, float g, float& m, float& v) {
+    if (s.weight_decay != 0.0f) g = g + s.weight_decay * p;      // grad.add(param, alpha=weight_decay)
+    m = m + s.one_minus_beta1 * (g - m);                         // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * s.beta2 + s.one_minus_beta2 * (g * g);               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+    const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;           // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    p = p + s.neg_step_size * (m / denom);                       // param.addcdiv_(exp_avg, denom, value=-step_size)
+}

@@ -182,7 +182,39 @@ int emul_sizeof(int which) {
         case 5: return (int)sizeof(NvrConfig);
         case 6: return (int)sizeof(NvrCounters);
         case 7: return (int)sizeof(NvrStageProfile);
+        case 8: return (int)sizeof(NvrAdamTensor);
     }
     return -1;
+}
+// get_rays + get_near_far per pixel, row-major, no compaction (the kernels k_rays_mask / k_rays_emit run exactly
+// these two calls per pixel); o = float32 camera origin.
+void emul_rays(int H, int W, const double* Kinv, const double* R, const double* T, const float* bounds, float* o,
+               float* ray_d, float* near_, float* far_, unsigned char* mask) {
+    CameraDev cam;
+    for (int i = 0; i < 9; ++i) { cam.Kinv[i] = Kinv[i]; cam.R[i] = R[i]; }
+    for (int a = 0; a < 3; ++a) {
+        cam.T[a] = T[a];
+        cam.o[a] = -((R[0 * 3 + a] * T[0] + R[1 * 3 + a] * T[1]) + R[2 * 3 + a] * T[2]);
+        o[a] = (float)cam.o[a];
+    }
+    for (int j = 0; j < H; ++j)
+        for (int i = 0; i < W; ++i) {
+            const long long pix = (long long)j * W + i;
+            nvr_pixel_ray(cam, i, j, ray_d + pix * 3);
+            mask[pix] = nvr_near_far(bounds, o, ray_d + pix * 3, near_ + pix, far_ + pix) ? 1 : 0;
+        }
+}
+
+// one Adam step over n elements with the scalars nvr_adam_step derives on the host
+void emul_adam(float* p, const float* g, float* m, float* v, long long n, long long step, double lr, double wd, double beta1,
+               double beta2, double eps) {
+    AdamScalars s;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    s.beta1 = (float)beta1; s.beta2 = (float)beta2;
+    s.one_minus_beta1 = (float)(1.0 - beta1); s.one_minus_beta2 = (float)(1.0 - beta2);
+    s.eps = (float)eps; s.weight_decay = (float)wd;
+    s.neg_step_size = (float)(-(lr / bc1));
+    s.bc2_sqrt = (float)sqrt(bc2);
+    for (long long i = 0; i < n; ++i) nvr_adam_update(s, p[i], g[i], m[i], v[i]);
 }
 }

@@ -24,8 +24,7 @@ from instant_nvr_b200 import cabi  # noqa: E402
 EMUL_DIR = os.path.join(REPO, "tests", "host_emul")
 
 
-@pytest.fixture(scope="module")
-def emul():
+def build_emul():
     so = os.path.join(EMUL_DIR, "libnvr_emul.so")
     src = os.path.join(EMUL_DIR, "emul.cpp")
     deps = [src, os.path.join(REPO, "instant_nvr_b200", "csrc", "nvr_math.cuh"), os.path.join(REPO, "include", "nvr_b200.h")]
@@ -34,13 +33,18 @@ def emul():
     return C.CDLL(so)
 
 
+@pytest.fixture(scope="module")
+def emul():
+    return build_emul()
+
+
 def fp(t):
     return C.c_void_p(t.data_ptr())
 
 
 def test_struct_sizes_match_header(emul):
     for which, cls in enumerate((cabi.NvrGrid, cabi.NvrLinear, cabi.NvrPart, cabi.NvrParams, cabi.NvrFrame,
-                                 cabi.NvrConfig, cabi.NvrCounters, cabi.NvrStageProfile)):
+                                 cabi.NvrConfig, cabi.NvrCounters, cabi.NvrStageProfile, cabi.NvrAdamTensor)):
         assert emul.emul_sizeof(which) == C.sizeof(cls), cls.__name__
 
 
