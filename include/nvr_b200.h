@@ -113,7 +113,8 @@ typedef struct NvrConfig {
     int32_t abi_version;           /* NVR_ABI_VERSION */
     int32_t device;                /* CUDA device ordinal */
     float smpl_thresh;             /* cfg.smpl_thresh */
-    int32_t mlp_mode;              /* 0: fp32 FFMA tiles (parity mode); 1: tcgen05 3xTF32 tensor-core tiles */
+    int32_t mlp_mode;              /* part MLPs: 0 fp32 FFMA tiles; 1 tcgen05 3xTF32 tiles, 256-thread CTAs; 2 the same with two
+                                      epilogue warpgroups per tile slot (512-thread CTAs) */
 } NvrConfig;
 
 /* Device-side work counters of the most recent pass (diagnostics / benchmark accounting). */

@@ -124,7 +124,8 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
         cudaMemset(h->d_counters_snapshot, 0, NVR_CTR_WORDS * sizeof(int)) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_CLUSTER_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mlp_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_deformer_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES) != cudaSuccess ||
         cudaMalloc(&h->d_part_mlp, NVR_PARTS * sizeof(PartMlpDev)) != cudaSuccess ||
@@ -295,6 +296,15 @@ static int grid_for(long long items, int per_block, int max_blocks) {
     return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
 }
 
+// tensor-core part MLPs over one part's pair list; mlp_mode 1: one epilogue warpgroup per tile slot, 2: two
+static void launch_mlp_tc(NvrEngine* h, int grid, const float* blk, int n_rgb, int part, const int* count, const PairRec* pl,
+                          const float* el, float4* raws, int out_stride, cudaStream_t st) {
+    if (h->cfg.mlp_mode == 2)
+        k_mlp_tc<2><<<grid, TC_THREADS(2), TC_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
+    else
+        k_mlp_tc<1><<<grid, TC_THREADS(1), TC_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
+}
+
 // One pass over `n` samples (n <= ws.cap): cull -> warp -> 5x(embed, mlp).  The caller resolves.
 static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const float* ray_d, const float* near_,
                     const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
@@ -311,7 +321,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     { StageTimer t(h, st, NVR_STAGE_WARP);
     k_warp<<<dim3(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS), WARP_THREADS, 0, st>>>(
         h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd); }
-    const bool tc = h->cfg.mlp_mode == 1;
+    const bool tc = h->cfg.mlp_mode >= 1;
     if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
         StageTimer t(h, st, NVR_STAGE_MLP);
         k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
@@ -331,8 +341,8 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         } }
         StageTimer t(h, st, NVR_STAGE_MLP);
         if (tc)
-            k_mlp_tc<<<grid_for(n, 256, sm), TC_THREADS, TC_SMEM_BYTES, st>>>(h->d_mlp_blocks + (size_t)p * TC_BLOCK_FLOATS, h->part_mlp[p].n_rgb, p,
-                                                                     w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
+            launch_mlp_tc(h, grid_for(n, 256, sm), h->d_mlp_blocks + (size_t)p * TC_BLOCK_FLOATS, h->part_mlp[p].n_rgb, p,
+                          w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS, st);
         else
             k_mlp<<<grid_for(n, MLP_TILE, sm), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[p], p, h->fdev.latent_index,
                                                                           w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
@@ -465,11 +475,11 @@ extern "C" int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const f
     if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_part_mlp: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
     k_make_pairs<<<(int)((n + 255) / 256), 256, 0, st>>>(dirs, (int)n, w.pairs, w.counters);
-    if (h->cfg.mlp_mode == 1) {
+    if (h->cfg.mlp_mode >= 1) {
         if (((uintptr_t)emb & 15) != 0) return fail(h, "nvr_part_mlp: emb must be 16-byte aligned (rows of 20 floats)");
         k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
-        k_mlp_tc<<<grid_for(n, 256, h->sm_count), TC_THREADS, TC_SMEM_BYTES, st>>>(h->d_mlp_blocks + (size_t)part * TC_BLOCK_FLOATS,
-                                                                           h->part_mlp[part].n_rgb, 0, w.counters, w.pairs, emb, (float4*)raw, 1);
+        launch_mlp_tc(h, grid_for(n, 256, h->sm_count), h->d_mlp_blocks + (size_t)part * TC_BLOCK_FLOATS, h->part_mlp[part].n_rgb, 0,
+                      w.counters, w.pairs, emb, (float4*)raw, 1, st);
         h->launches++;
     } else {
         k_mlp<<<grid_for(n, MLP_TILE, h->sm_count), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[part], 0, h->fdev.latent_index, w.counters,

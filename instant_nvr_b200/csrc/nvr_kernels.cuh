@@ -35,7 +35,7 @@ struct FrameDev {                  // per-frame tensors as the kernels see them
     const float* Th;
     VolumeDev dist;                // compact (D,H,W,1) distance volume
     VolumeDev tuv;                 // (D',H',W',2)
-    const float4* verts;           // part vertices, spatially sorted, NVR_CL per cluster (x, y, z, orig index)
+    const float4* verts;           // part vertices, spatially sorted: one 16-float4 SoA block per cluster (x | y | z | orig index)
     const float4* cl_lo;           // per-cluster AABB
     const float4* cl_hi;
     const int* cl_off;             // [6] cluster offsets per part (device)
@@ -195,7 +195,10 @@ k_cluster_apply(const float* __restrict__ part_pts, int maxlen, const int* __res
             const float* s = part_pts + ((long long)part * maxlen + j) * 3;
             x = s[0]; y = s[1]; z = s[2];
         }
-        if (in) verts[(long long)c * NVR_CL + lane16] = make_float4(x, y, z, __int_as_float(j >= 0 ? j : 0));
+        if (in) {                                                  // structure-of-arrays cluster block (nvr_knn_scan)
+            float* blk = reinterpret_cast<float*>(verts + (long long)c * NVR_CL);
+            blk[lane16] = x; blk[16 + lane16] = y; blk[32 + lane16] = z; blk[48 + lane16] = __int_as_float(j >= 0 ? j : 0);
+        }
         float lo[3] = {x, y, z}, hi[3] = {j >= 0 ? x : -INFINITY, j >= 0 ? y : -INFINITY, j >= 0 ? z : -INFINITY};
         int cnt = j >= 0 ? 1 : 0;
 #pragma unroll
@@ -277,7 +280,7 @@ __device__ __forceinline__ void knn_part_group(const FrameDev& fr, int part, con
             m &= m - 1;
             const float lb = nvr_aabb_lb(__ldg(fr.cl_lo + c0 + cc), __ldg(fr.cl_hi + c0 + cc), p);
             const bool need = live && !(lb * NVR_PRUNE_SLACK > nvr_knn_d2(k, 3));
-            if (__any_sync(0xffffffffu, need)) nvr_knn_scan(fr.verts + (long long)(c0 + cc) * NVR_CL, NVR_CL, p, k);
+            if (__any_sync(0xffffffffu, need)) nvr_knn_scan(fr.verts + (long long)(c0 + cc) * NVR_CL, p, k);
         }
     }
 }
@@ -410,21 +413,15 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, const float4* __res
 // warp: neighbour records -> canonical-space pairs (blend, LBS, deformer); blockIdx.y = part
 // -----------------------------------------------------------------------------------------
 #define WARP_THREADS 128
-#define WARP_SMEM_FLOATS (32 * 19 + 32 + 32 * 32 + 32 + 3 * 32 + 4 + 2 * NVR_JOINTS * 16 + 32 * WARP_THREADS)
-struct DeformerSmem { DeformerMlp dm; float* A; float* bigA; float* scratch; };
+#define WARP_SMEM_FLOATS (NVR_DEF_PACKED_FLOATS + 2 * NVR_JOINTS * 16 + 32 * WARP_THREADS)
+struct DeformerSmem { const float* pk; float* A; float* bigA; float* scratch; };
 __device__ __forceinline__ DeformerSmem stage_deformer(float* sm, const DeformerMlp& g, const float* A, const float* bigA) {
-    float* sw0 = sm; float* sb0 = sw0 + 32 * 19; float* sw1 = sb0 + 32; float* sb1 = sw1 + 32 * 32;
-    float* sw2 = sb1 + 32; float* sb2 = sw2 + 3 * 32; float* sA = sb2 + 4; float* sB = sA + NVR_JOINTS * 16;
-    for (int i = threadIdx.x; i < 32 * 19; i += blockDim.x) sw0[i] = g.w0[i];
-    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) sw1[i] = g.w1[i];
-    for (int i = threadIdx.x; i < 3 * 32; i += blockDim.x) sw2[i] = g.w2[i];
-    if (threadIdx.x < 32) { sb0[threadIdx.x] = g.b0[threadIdx.x]; sb1[threadIdx.x] = g.b1[threadIdx.x]; }
-    if (threadIdx.x < 3) sb2[threadIdx.x] = g.b2[threadIdx.x];
+    float* sA = sm + NVR_DEF_PACKED_FLOATS; float* sB = sA + NVR_JOINTS * 16;
+    nvr_pack_deformer(g, sm, threadIdx.x, blockDim.x);
     if (A) for (int i = threadIdx.x; i < NVR_JOINTS * 16; i += blockDim.x) { sA[i] = A[i]; sB[i] = bigA[i]; }
     __syncthreads();
     DeformerSmem d;
-    d.dm = DeformerMlp{sw0, sb0, sw1, sb1, sw2, sb2};
-    d.A = sA; d.bigA = sB; d.scratch = sB + NVR_JOINTS * 16;
+    d.pk = sm; d.A = sA; d.bigA = sB; d.scratch = sB + NVR_JOINTS * 16;
     return d;
 }
 
@@ -451,7 +448,7 @@ k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs
         float d[3], x0[3], v[3], r[3];
         nvr_dir_to_pose(fr.R, wd, d);
         nvr_blend_lbs(rec.idx, rec.w, pbw_part, ds.A, ds.bigA, p, d, x0, v);
-        nvr_deformer_point(dg, ds.dm, fr.tuv, frame_dim, x0, r, sc, WARP_THREADS);
+        nvr_deformer_point(dg, ds.pk, fr.tuv, frame_dim, x0, r, sc, WARP_THREADS);
         PairRec out;
         out.x = x0[0] + r[0]; out.y = x0[1] + r[1]; out.z = x0[2] + r[2];   // :113
         out.vx = v[0]; out.vy = v[1]; out.vz = v[2];
@@ -479,7 +476,7 @@ k_deformer(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float x0[3] = {x[i * 3], x[i * 3 + 1], x[i * 3 + 2]};
         float r[3];
-        nvr_deformer_point(dg, ds.dm, fr.tuv, frame_dim, x0, r, sc, WARP_THREADS);
+        nvr_deformer_point(dg, ds.pk, fr.tuv, frame_dim, x0, r, sc, WARP_THREADS);
         out[i * 3] = r[0]; out[i * 3 + 1] = r[1]; out[i * 3 + 2] = r[2];
     }
 }
@@ -567,16 +564,17 @@ k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restr
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = ld_sector(tab + (unsigned long long)row[c] * 16 + half * 8);
             const float wx[2] = {1.0f - of[0], of[0]}, wy[2] = {1.0f - of[1], of[1]}, wz[2] = {1.0f - of[2], of[2]};
-            float acc[8];
+            F2 acc[4];
 #pragma unroll
-            for (int f = 0; f < 8; ++f) acc[f] = 0.0f;
+            for (int f = 0; f < 4; ++f) acc[f] = F2{0.0f, 0.0f};
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float w = (wx[(c >> 2) & 1] * wy[(c >> 1) & 1]) * wz[c & 1];      // :158-159
+                const F2 w2 = {w, w};
 #pragma unroll
-                for (int f = 0; f < 8; ++f) acc[f] += w * v[c].v[f];                    // :160
+                for (int f = 0; f < 4; ++f) nvr_fma2(acc[f], w2, F2{v[c].v[2 * f], v[c].v[2 * f + 1]});   // :160, two features per FFMA2
             }
-            float sfeat = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            float sfeat = ((acc[0].x + acc[0].y) + (acc[1].x + acc[1].y)) + ((acc[2].x + acc[2].y) + (acc[3].x + acc[3].y));
             sfeat += __shfl_xor_sync(0xffffffffu, sfeat, 1);                            // :165 sum over the 16 features
             if (live && half == (l & 1)) o[3 + l] = sfeat;
         }

@@ -23,6 +23,56 @@ struct float4 { float x, y, z, w; };      // host emulation only
 #define NVR_JOINTS 24
 #define NVR_KNN 4
 
+// Two fp32 fused multiply-adds in one instruction (Blackwell FFMA2, PTX fma.rn.f32x2): c = a * b + c per half,
+// each half rounded once like fmaf.  Halves the issue slots of the FMA-heavy inner loops; the host build (tests)
+// evaluates the same two products separately.
+struct F2 { float x, y; };
+NVR_HD void nvr_fma2(F2& c, const F2& a, const F2& b) {
+#ifdef __CUDA_ARCH__
+    unsigned long long ua, ub, uc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(uc) : "l"(ua), "l"(ub));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(uc));
+#else
+    c.x = a.x * b.x + c.x;
+    c.y = a.y * b.y + c.y;
+#endif
+}
+NVR_HD F2 nvr_sub2(const F2& a, const F2& b) {                    // FADD2
+#ifdef __CUDA_ARCH__
+    unsigned long long ua, ub, ur;
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(ur) : "l"(ua), "l"(ub));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(ur));
+    return r;
+#else
+    return F2{a.x - b.x, a.y - b.y};
+#endif
+}
+NVR_HD F2 nvr_mul2(const F2& a, const F2& b) {                    // FMUL2
+#ifdef __CUDA_ARCH__
+    unsigned long long ua, ub, ur;
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ur) : "l"(ua), "l"(ub));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(ur));
+    return r;
+#else
+    return F2{a.x * b.x, a.y * b.y};
+#endif
+}
+// warp vote on the device (callers are warp-converged), identity in the scalar host build
+#ifdef __CUDA_ARCH__
+#define NVR_ANY(x) __any_sync(0xffffffffu, (x))
+#else
+#define NVR_ANY(x) (x)
+#endif
+
 // Device-side view of one grid (mirrors NvrGrid, plus the Barrett constant for `% T`).
 struct GridDev {
     const float* dense;
@@ -275,41 +325,43 @@ NVR_HD float4 nvr_ld_vert(const float4* v) {
     return *v;
 #endif
 }
-NVR_HD int nvr_vert_id(const float4& v) {
+NVR_HD int nvr_f2i(float f) {
 #ifdef __CUDA_ARCH__
-    return __float_as_int(v.w);
+    return __float_as_int(f);
 #else
-    int id; memcpy(&id, &v.w, 4); return id;
+    int id; memcpy(&id, &f, 4); return id;
 #endif
 }
 
-// verts: (x, y, z, bit pattern of the ORIGINAL vertex index) of one run of vertices.  Exact.
-// Vertices are taken four at a time: when none of the four can enter, a group costs the distance
-// arithmetic plus one compare and one branch.
-NVR_HD void nvr_knn_scan(const float4* verts, int count, const float p[3], Knn4& k) {
-    int j = 0;
+// One cluster = NVR_CL (16) vertices stored as a 16-float4 structure-of-arrays block:
+//     blk[0..3] = x of vertices 0..15, blk[4..7] = y, blk[8..11] = z, blk[12..15] = bit patterns of the ORIGINAL
+//     vertex indices; padding slots hold x = y = z = +inf (distance +inf, never admitted ahead of a real vertex).
+// Vertices are taken four at a time with the x/y/z differences, squares and sums of TWO vertices per packed
+// instruction (FADD2 / FMUL2 / FFMA2).  On the device all 32 lanes of the warp must call this together: a group
+// of four costs the distance arithmetic plus one vote when no lane can use it, and each candidate is inserted
+// (branch-free, per lane) only when some lane admits it.  Exact: the result is the 4 smallest (d2, index) keys.
+NVR_HD void nvr_knn_scan(const float4* blk, const float p[3], Knn4& k) {
+    const F2 px = {p[0], p[0]}, py = {p[1], p[1]}, pz = {p[2], p[2]};
 #pragma unroll 2
-    for (; j + 4 <= count; j += 4) {
-        const float4 a = nvr_ld_vert(verts + j), b = nvr_ld_vert(verts + j + 1), c = nvr_ld_vert(verts + j + 2),
-                     d = nvr_ld_vert(verts + j + 3);
-        const float da = nvr_dist2(p, a), db = nvr_dist2(p, b), dc = nvr_dist2(p, c), dd = nvr_dist2(p, d);
-        if (nvr_knn_admits(k, fminf(fminf(da, db), fminf(dc, dd)))) {
-            if (nvr_knn_admits(k, da)) nvr_knn_insert(k, da, nvr_vert_id(a));
-            if (nvr_knn_admits(k, db)) nvr_knn_insert(k, db, nvr_vert_id(b));
-            if (nvr_knn_admits(k, dc)) nvr_knn_insert(k, dc, nvr_vert_id(c));
-            if (nvr_knn_admits(k, dd)) nvr_knn_insert(k, dd, nvr_vert_id(d));
+    for (int q = 0; q < 4; ++q) {
+        const float4 x = nvr_ld_vert(blk + q), y = nvr_ld_vert(blk + 4 + q), z = nvr_ld_vert(blk + 8 + q), id = nvr_ld_vert(blk + 12 + q);
+        const F2 dx0 = nvr_sub2(px, F2{x.x, x.y}), dx1 = nvr_sub2(px, F2{x.z, x.w});
+        const F2 dy0 = nvr_sub2(py, F2{y.x, y.y}), dy1 = nvr_sub2(py, F2{y.z, y.w});
+        const F2 dz0 = nvr_sub2(pz, F2{z.x, z.y}), dz1 = nvr_sub2(pz, F2{z.z, z.w});
+        F2 d0 = nvr_mul2(dx0, dx0), d1 = nvr_mul2(dx1, dx1);
+        nvr_fma2(d0, dy0, dy0); nvr_fma2(d1, dy1, dy1);
+        nvr_fma2(d0, dz0, dz0); nvr_fma2(d1, dz1, dz1);           // squared L2, as knn_points returns it
+        if (NVR_ANY(nvr_knn_admits(k, fminf(fminf(d0.x, d0.y), fminf(d1.x, d1.y))))) {
+            if (NVR_ANY(nvr_knn_admits(k, d0.x))) { if (nvr_knn_admits(k, d0.x)) nvr_knn_insert(k, d0.x, nvr_f2i(id.x)); }
+            if (NVR_ANY(nvr_knn_admits(k, d0.y))) { if (nvr_knn_admits(k, d0.y)) nvr_knn_insert(k, d0.y, nvr_f2i(id.y)); }
+            if (NVR_ANY(nvr_knn_admits(k, d1.x))) { if (nvr_knn_admits(k, d1.x)) nvr_knn_insert(k, d1.x, nvr_f2i(id.z)); }
+            if (NVR_ANY(nvr_knn_admits(k, d1.y))) { if (nvr_knn_admits(k, d1.y)) nvr_knn_insert(k, d1.y, nvr_f2i(id.w)); }
         }
-    }
-#pragma unroll 1
-    for (; j < count; ++j) {
-        const float4 v = nvr_ld_vert(verts + j);
-        const float d2 = nvr_dist2(p, v);
-        if (nvr_knn_admits(k, d2)) nvr_knn_insert(k, d2, nvr_vert_id(v));
     }
 }
 
-// Lower bound of nvr_dist2(p, v) over every v inside the box [lo, hi].  Each fp32 operation in
-// nvr_dist2 is monotone in |p - v| per axis, so the same expression on the per-axis gap is a lower
+// Lower bound of the scan's distance over every v inside the box [lo, hi].  Each fp32 operation of the
+// distance is monotone in |p - v| per axis, so the same expression on the per-axis gap is a lower
 // bound up to the contraction (fma vs mul+add) the compiler picks; callers prune with a 1e-6
 // relative slack for that.
 NVR_HD float nvr_aabb_lb(const float4& lo, const float4& hi, const float p[3]) {
@@ -417,18 +469,22 @@ NVR_HD void nvr_lbs_to_bigpose(const float bw[NVR_JOINTS], const float* A, const
 // 24 weights never exist as an array and the joint loop stays rolled (small code, no local memory).
 NVR_HD void nvr_blend_lbs(const int idx[NVR_KNN], const float w[NVR_KNN], const float* pbw_part, const float* A,
                           const float* bigA, const float p[3], const float d[3], float x0[3], float v[3]) {
-    float M[12], B[12];
+    F2 M2[6], B2[6];                                              // element pairs (e, e+1): two FMAs per FFMA2
 #pragma unroll
-    for (int e = 0; e < 12; ++e) { M[e] = 0.0f; B[e] = 0.0f; }
+    for (int e = 0; e < 6; ++e) { M2[e] = F2{0.0f, 0.0f}; B2[e] = F2{0.0f, 0.0f}; }
 #pragma unroll 2
     for (int j = 0; j < NVR_JOINTS; ++j) {
         const float bj = nvr_blend_joint(idx, w, pbw_part, j);
+        const F2 b2 = {bj, bj};
 #pragma unroll
-        for (int e = 0; e < 12; ++e) {
-            M[e] += bj * A[j * 16 + e];
-            B[e] += bj * bigA[j * 16 + e];
+        for (int e = 0; e < 6; ++e) {
+            nvr_fma2(M2[e], b2, F2{A[j * 16 + 2 * e], A[j * 16 + 2 * e + 1]});
+            nvr_fma2(B2[e], b2, F2{bigA[j * 16 + 2 * e], bigA[j * 16 + 2 * e + 1]});
         }
     }
+    float M[12], B[12];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { M[2 * e] = M2[e].x; M[2 * e + 1] = M2[e].y; B[2 * e] = B2[e].x; B[2 * e + 1] = B2[e].y; }
     nvr_lbs_apply(M, B, p, d, x0, v);
 }
 
@@ -452,54 +508,75 @@ NVR_HD void nvr_posenc27(const float v[3], float* out) {
 // ---------------------------------------------------------------------------------------
 // UV-time deformer                                              uv_deformer.py:23-45
 // ---------------------------------------------------------------------------------------
-// Weights are read through plain pointers (global or shared memory; row-major (out,in)).
+// DeformerMlp: the nn.Linear tensors as they are stored (row-major (out,in)).  The forward reads a PACKED copy
+// (shared memory on the device) laid out for 16-byte loads and paired FMAs:
+//     w0p [32][20] = [W0 row (19) | b0]   (the input row gets a constant 1 in column 19)
+//     w1  [32][32], b1 [32], w2 [3][32], b2 [3] (+1 pad)
 struct DeformerMlp {
     const float *w0, *b0, *w1, *b1, *w2, *b2;    // 32x19, 32, 32x32, 32, 3x32, 3
 };
+#define NVR_DEF_W0P 0
+#define NVR_DEF_W1 (32 * 20)
+#define NVR_DEF_B1 (NVR_DEF_W1 + 32 * 32)
+#define NVR_DEF_W2 (NVR_DEF_B1 + 32)
+#define NVR_DEF_B2 (NVR_DEF_W2 + 3 * 32)
+#define NVR_DEF_PACKED_FLOATS (NVR_DEF_B2 + 4)
+// thread `tid` of `nthreads` writes its share of the packed block (host: tid 0 of 1)
+NVR_HD void nvr_pack_deformer(const DeformerMlp& m, float* out, int tid, int nthreads) {
+    for (int i = tid; i < 32 * 20; i += nthreads) {
+        const int o = i / 20, k = i - o * 20;
+        out[NVR_DEF_W0P + i] = k < 19 ? m.w0[o * 19 + k] : m.b0[o];
+    }
+    for (int i = tid; i < 32 * 32; i += nthreads) out[NVR_DEF_W1 + i] = m.w1[i];
+    for (int i = tid; i < 32; i += nthreads) out[NVR_DEF_B1 + i] = m.b1[i];
+    for (int i = tid; i < 3 * 32; i += nthreads) out[NVR_DEF_W2 + i] = m.w2[i];
+    for (int i = tid; i < 4; i += nthreads) out[NVR_DEF_B2 + i] = i < 3 ? m.b2[i] : 0.0f;
+}
 
-// sc: 32 scratch floats of THIS thread, element stride ss (shared memory on the device: sc = base + tid,
-// ss = block size, so neighbouring lanes hit neighbouring banks; a plain array with ss = 1 on the host).
-// The output loops stay rolled -- the activations live in the scratch row instead of 64 registers --
-// which keeps the kernel's code inside the instruction cache.
-NVR_HD void nvr_deformer_point(const GridDev& g, const DeformerMlp& m, const VolumeDev& tuv, float frame_dim,
+// sum_k w[k] x[k] over K (a multiple of 4) inputs held in registers, weights by 16-byte loads; even / odd k
+// accumulate in the two halves of one FFMA2 accumulator (fp32 re-association against a sequential sum: the
+// reference's own sgemm does not promise an order either).
+template <int K>
+NVR_HD float nvr_dot_packed(const float* w, const float* x, float init) {
+    F2 acc = {init, 0.0f};
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(w + 4 * q);
+        nvr_fma2(acc, F2{t.x, t.y}, F2{x[4 * q], x[4 * q + 1]});
+        nvr_fma2(acc, F2{t.z, t.w}, F2{x[4 * q + 2], x[4 * q + 3]});
+    }
+    return acc.x + acc.y;
+}
+
+// pk: the packed block (see above).  sc: 32 scratch floats of THIS thread, element stride ss (shared memory on the
+// device: sc = base + tid, ss = block size, so neighbouring lanes hit neighbouring banks; a plain array with
+// ss = 1 on the host).  The output loops stay rolled -- the activations live in the scratch row instead of 64
+// registers -- which keeps the kernel's code inside the instruction cache.
+NVR_HD void nvr_deformer_point(const GridDev& g, const float* pk, const VolumeDev& tuv, float frame_dim,
                                const float x0[3], float resd[3], float* sc, int ss) {
     float uvt[3];
     nvr_sample_volume(tuv, x0, 0, 2, uvt);                        // pts_sample_uv :32
     uvt[2] = frame_dim;                                           // :35
     nvr_embed_point<2>(g, uvt, sc, ss);                           // :37 (8 levels x 2 features, concat) -> sc[0..18]
     {
-        float e[19];
+        float e[20];
 #pragma unroll
         for (int i = 0; i < 19; ++i) e[i] = sc[i * ss];
+        e[19] = 1.0f;                                             // picks up b0 from column 19 of w0p
 #pragma unroll 1
-        for (int o = 0; o < 32; ++o) {
-            float acc = m.b0[o];
-#pragma unroll
-            for (int i = 0; i < 19; ++i) acc += m.w0[o * 19 + i] * e[i];
-            sc[o * ss] = nvr_softplus_hidden(acc);
-        }
+        for (int o = 0; o < 32; ++o) sc[o * ss] = nvr_softplus_hidden(nvr_dot_packed<20>(pk + NVR_DEF_W0P + o * 20, e, 0.0f));
     }
+    float h[32];
     {
-        float h1[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) h1[i] = sc[i * ss];
+        for (int i = 0; i < 32; ++i) h[i] = sc[i * ss];
 #pragma unroll 1
-        for (int o = 0; o < 32; ++o) {
-            float acc = m.b1[o];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc += m.w1[o * 32 + i] * h1[i];
-            sc[o * ss] = nvr_softplus_hidden(acc);
-        }
-    }
-    float acc[3] = {m.b2[0], m.b2[1], m.b2[2]};
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-        const float h = sc[i * ss];
-#pragma unroll
-        for (int o = 0; o < 3; ++o) acc[o] += m.w2[o * 32 + i] * h;
+        for (int o = 0; o < 32; ++o) sc[o * ss] = nvr_softplus_hidden(nvr_dot_packed<32>(pk + NVR_DEF_W1 + o * 32, h, pk[NVR_DEF_B1 + o]));
     }
 #pragma unroll
-    for (int o = 0; o < 3; ++o) resd[o] = 0.05f * tanhf(acc[o]);  // :39
+    for (int i = 0; i < 32; ++i) h[i] = sc[i * ss];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) resd[o] = 0.05f * tanhf(nvr_dot_packed<32>(pk + NVR_DEF_W2 + o * 32, h, pk[NVR_DEF_B2 + o]));   // :39
 }
 
 // ---------------------------------------------------------------------------------------

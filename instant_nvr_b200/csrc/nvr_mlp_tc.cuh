@@ -2,9 +2,10 @@
 //
 //   k_mlp_prep   per render, one CTA per part: repack the part's Linear weights into the tcgen05 operand
 //                panels (3xTF32 split: hi = top 19 bits, lo = w - hi) and fold what can be folded
-//   k_mlp_tc     persistent, one CTA (256 threads = two 128-pair tile slots) per SM; weight panels and the
-//                input tile in shared memory, hidden activations + accumulators in TMEM, tcgen05.mma
-//                kind::tf32 issued by one thread per slot
+//   k_mlp_tc<H>  persistent, one CTA (two 128-pair tile slots x H epilogue warpgroups of 128 threads) per SM;
+//                weight panels and the input tile in shared memory, hidden activations + accumulators in
+//                TMEM, tcgen05.mma kind::tf32 issued by one thread per slot.  H = 2 (512 threads): two
+//                warps share each 32-lane TMEM quarter of a slot and split the 64 activation columns
 //
 // Algebra.  Reference, per pair (e = grid embedding 19, pe = PosEnc(dir) 27, lat = latent row 8):
 //     h    = softplus(W0 e + b0)                       64
@@ -175,18 +176,24 @@ __device__ __forceinline__ void tmem_st16_split(uint32_t t_hi, uint32_t t_lo, co
 }
 
 // ---- shared memory and TMEM plan ------------------------------------------------------------------
-// A CTA runs TWO tile slots (warps 0-3 and 4-7), each with its own 128-pair tile in flight, so one
-// slot's tensor-core GEMMs overlap the other slot's activation epilogue.  The slots share the weight
+// A CTA runs TWO tile slots, each with its own 128-pair tile in flight, so one slot's tensor-core GEMMs
+// overlap the other slot's activation epilogue.  Warp w works for slot (w >> 2) & 1 on TMEM lanes
+// 32 (w & 3) .. +31 (the hardware's lane window of a warp) and, with H = 2 warpgroups per slot, on activation
+// columns 32 (w >> 3) .. +31: the epilogue (tcgen05.ld -> bias + softplus -> hi/lo split -> tcgen05.st) is
+// latency-bound at 2 warps per scheduler (ncu r1f: issue 37 %, tensor pipe 26 %), so the second warpgroup
+// per slot nearly doubles what the tensor pipe is fed.  The partial dot products of the two skinny layers
+// (o[0], rgb) cross between the halves through 4 floats per row of shared memory.  The slots share the weight
 // panels; each owns an X operand buffer in shared memory and 192 TMEM columns:
 //     smem  X_hi / X_lo   [48/4 chunks][128 rows][4] floats each (the same K-major interleaved layout as B)
 //     TMEM  [0,64) H_hi  [64,128) H_lo  (hidden activations, A operand of the next GEMM)  [128,192) D
 // GEMM 0 accumulates into the H_hi columns (H is dead then); GEMM 3 into D (consumed by then).
-#define TC_THREADS 256
+#define TC_THREADS(H) (256 * (H))
 #define TC_XPANEL (TC_KX * 128)                                  // floats per X panel
 #define TC_SM_X (TC_BLOCK_FLOATS)                                // [slot][hi|lo][TC_XPANEL]
 #define TC_SM_BAR (TC_SM_X + 4 * TC_XPANEL)                      // 2 mbarriers (4 floats), tmem base (1)
+#define TC_SM_EX (TC_SM_BAR + 8)                                 // [slot][128 rows][4]: o0 / rgb partials of the 2nd half
 #undef TC_SMEM_BYTES
-#define TC_SMEM_BYTES ((TC_SM_BAR + 8) * 4)
+#define TC_SMEM_BYTES ((TC_SM_EX + 2 * 128 * 4) * 4)
 #define TC_SLOT_COLS 192
 #define TC_COL_HHI 0
 #define TC_COL_HLO 64
@@ -249,10 +256,12 @@ __device__ __forceinline__ void posenc27_doubling(const float v[3], float* out) 
         }
     }
 }
-__device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+template <int H>
+__device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(128 * H) : "memory"); }
 
 // One launch per part.  blk = that part's packed block; pl / el = its pair list and embedding rows.
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int H>
+__global__ void __launch_bounds__(TC_THREADS(H), 1)
 k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restrict__ count_dev, const PairRec* __restrict__ pl,
          const float* __restrict__ el, float4* __restrict__ raws, int out_stride) {
     extern __shared__ __align__(128) float sm[];
@@ -261,7 +270,10 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
     if ((int)blockIdx.x * 2 >= n_tiles) return;                     // block-uniform, before any allocation
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TC_SM_BAR);
     uint32_t* tbase_slot = reinterpret_cast<uint32_t*>(sm + TC_SM_BAR + 4);
-    const int tid = threadIdx.x, warp = tid >> 5, slot = warp >> 2, stid = tid & 127;
+    const int tid = threadIdx.x, warp = tid >> 5, slot = (warp >> 2) & 1, half = warp >> 3, stid = tid & 127;
+    constexpr int CPH = 4 / H;                                      // 16-column chunks per half
+    const bool lead = half == 0;
+    float* ex = sm + TC_SM_EX + (slot * 128 + stid) * 4;
     {   // weights -> shared memory (float4 copies; the block is 16-byte aligned by construction)
         const float4* src = reinterpret_cast<const float4*>(blk);
         float4* dst = reinterpret_cast<float4*>(sm);
@@ -309,6 +321,7 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
             x[46] = 0.0f; x[47] = 0.0f;
 #pragma unroll
             for (int c = 0; c < TC_KX / 4; ++c) {
+                if (H == 2 && (c & 1) != half) continue;            // the halves interleave the 16-byte chunks
                 float4 h4, l4;
                 h4.x = tf32_hi(x[c * 4]); h4.y = tf32_hi(x[c * 4 + 1]); h4.z = tf32_hi(x[c * 4 + 2]); h4.w = tf32_hi(x[c * 4 + 3]);
                 l4.x = x[c * 4] - h4.x; l4.y = x[c * 4 + 1] - h4.y; l4.z = x[c * 4 + 2] - h4.z; l4.w = x[c * 4 + 3] - h4.w;
@@ -318,18 +331,18 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();                                           // also orders the previous tile's TMEM reads
-        slot_sync(slot);
+        slot_sync<H>(slot);
         // ---- GEMM 0: h_pre = W0 e     (accumulator in the H_hi columns)
-        if (stid == 0) {
+        if (stid == 0 && lead) {
             tc_fence_after();
             gemm3_ss(tbase + TC_COL_HHI, s_xhi, s_xlo, s_p0, TC_K0, TC_K0, idesc, true);
             umma_commit(bar_a);
         }
         mbar_wait(bar_a, phase); phase ^= 1;
         tc_fence_after();
-        float o0 = sc[0];
+        float o0 = lead ? sc[0] : 0.0f;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = half * CPH; c < half * CPH + CPH; ++c) {
             float h[16];
             tmem_ld16(trow + TC_COL_HHI + c * 16, h);
             tmem_wait_ld();
@@ -340,12 +353,14 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
             }
             tmem_st16_split(trow + TC_COL_HHI + c * 16, trow + TC_COL_HLO + c * 16, h);
         }
-        const float occ = 1.0f - expf(-nvr_softplus(o0));           // :51
+        if (H == 2 && !lead) ex[0] = o0;
         tmem_wait_st();
         tc_fence_before();
-        slot_sync(slot);
+        slot_sync<H>(slot);
+        if (H == 2 && lead) o0 += ex[0];
+        const float occ = 1.0f - expf(-nvr_softplus(o0));           // :51 (used by the lead half only)
         // ---- GEMM 2: g_pre = W2x x + M h
-        if (stid == 0) {
+        if (stid == 0 && lead) {
             tc_fence_after();
             gemm3_ss(tbase + TC_COL_D, s_xhi, s_xlo, s_px, TC_KX, TC_KX, idesc, true);
             gemm3_ts(tbase + TC_COL_D, tbase + TC_COL_HHI, tbase + TC_COL_HLO, s_pm, TC_KH, idesc, false);
@@ -353,10 +368,10 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
         }
         mbar_wait(bar_a, phase); phase ^= 1;
         tc_fence_after();
-        float r[3] = {sc[1], sc[2], sc[3]};
+        float r[3] = {lead ? sc[1] : 0.0f, lead ? sc[2] : 0.0f, lead ? sc[3] : 0.0f};
         if (three) {                                                // block-uniform
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = half * CPH; c < half * CPH + CPH; ++c) {
                 float g[16];
                 tmem_ld16(trow + TC_COL_D + c * 16, g);
                 tmem_wait_ld();
@@ -366,9 +381,9 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
             }
             tmem_wait_st();
             tc_fence_before();
-            slot_sync(slot);
+            slot_sync<H>(slot);
             // ---- GEMM 3: W3 g   (accumulator back in D: GEMM 2's result has been consumed)
-            if (stid == 0) {
+            if (stid == 0 && lead) {
                 tc_fence_after();
                 gemm3_ts(tbase + TC_COL_D, tbase + TC_COL_HHI, tbase + TC_COL_HLO, s_p3, TC_KH, idesc, true);
                 umma_commit(bar_a);
@@ -379,7 +394,7 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
         const float* bl = three ? b3 : b2;
         // ---- last hidden activation + rgb = sigmoid(W4 g + b4)   (:58), raw = [rgb, occ] (:60)
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = half * CPH; c < half * CPH + CPH; ++c) {
             float g[16];
             tmem_ld16(trow + TC_COL_D + c * 16, g);
             tmem_wait_ld();
@@ -389,7 +404,13 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
                 r[0] += w4[c * 16 + k] * a; r[1] += w4[64 + c * 16 + k] * a; r[2] += w4[128 + c * 16 + k] * a;
             }
         }
-        if (row < n)
+        if (H == 2) {                                               // second half hands its partial rgb sums over
+            if (!lead) { ex[1] = r[0]; ex[2] = r[1]; ex[3] = r[2]; }
+            tc_fence_before();                                      // its TMEM reads precede the next tile's MMAs too
+            slot_sync<H>(slot);
+            if (lead) { r[0] += ex[1]; r[1] += ex[2]; r[2] += ex[3]; }
+        }
+        if (lead && row < n)
             raws[(long long)surv * out_stride + part] = make_float4(nvr_sigmoid(r[0]), nvr_sigmoid(r[1]), nvr_sigmoid(r[2]), occ);
     }
     tc_fence_before();

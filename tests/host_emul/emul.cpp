@@ -90,12 +90,16 @@ static HostClusters build_clusters(const float* src, int n) {
     std::vector<int> ids(n);
     for (int j = 0; j < n; ++j) ids[j] = j;
     kd_split(src, ids, 0, ncl);
-    hc.verts.assign((size_t)ncl * NVR_CL, float4{INFINITY, INFINITY, INFINITY, idx_bits(0)});
+    // one structure-of-arrays block per cluster: x[16] | y[16] | z[16] | index bits[16]  (k_cluster_apply)
+    hc.verts.assign((size_t)ncl * NVR_CL, float4{INFINITY, INFINITY, INFINITY, INFINITY});
+    for (int c = 0; c < ncl; ++c) for (int s = 0; s < NVR_CL; ++s) ((float*)&hc.verts[(size_t)c * NVR_CL])[48 + s] = idx_bits(0);
     hc.lo.assign(ncl, float4{INFINITY, INFINITY, INFINITY, 0.f});
     hc.hi.assign(ncl, float4{-INFINITY, -INFINITY, -INFINITY, 0.f});
     for (int i = 0; i < n; ++i) {
         const int j = ids[i], c = i / NVR_CL;
-        hc.verts[i] = float4{src[j * 3], src[j * 3 + 1], src[j * 3 + 2], idx_bits(j)};
+        float* blk = (float*)&hc.verts[(size_t)c * NVR_CL];
+        const int slot = i % NVR_CL;
+        blk[slot] = src[j * 3]; blk[16 + slot] = src[j * 3 + 1]; blk[32 + slot] = src[j * 3 + 2]; blk[48 + slot] = idx_bits(j);
         hc.lo[c].x = fminf(hc.lo[c].x, src[j * 3]); hc.hi[c].x = fmaxf(hc.hi[c].x, src[j * 3]);
         hc.lo[c].y = fminf(hc.lo[c].y, src[j * 3 + 1]); hc.hi[c].y = fmaxf(hc.hi[c].y, src[j * 3 + 1]);
         hc.lo[c].z = fminf(hc.lo[c].z, src[j * 3 + 2]); hc.hi[c].z = fmaxf(hc.hi[c].z, src[j * 3 + 2]);
@@ -115,8 +119,15 @@ void emul_knn_lbs(const float* part_pts, const float* part_pbw, const long long*
     for (int part = 0; part < NVR_PARTS; ++part) {
         const int cnt = (int)lengths2[part];
         const float* src = part_pts + (long long)part * maxlen * 3;
-        std::vector<float4> verts(cnt);
-        for (int j = 0; j < cnt; ++j) verts[j] = float4{src[j * 3], src[j * 3 + 1], src[j * 3 + 2], idx_bits(j)};
+        // brute force: the vertices in their original order, cut into blocks of 16 (+inf padding)
+        const int nblk = (cnt + NVR_CL - 1) / NVR_CL;
+        std::vector<float4> verts((size_t)nblk * NVR_CL, float4{INFINITY, INFINITY, INFINITY, INFINITY});
+        for (int j = 0; j < nblk * NVR_CL; ++j) {
+            float* blk = (float*)&verts[(size_t)(j / NVR_CL) * NVR_CL];
+            const int slot = j % NVR_CL;
+            if (j < cnt) { blk[slot] = src[j * 3]; blk[16 + slot] = src[j * 3 + 1]; blk[32 + slot] = src[j * 3 + 2]; }
+            blk[48 + slot] = idx_bits(j < cnt ? j : 0);
+        }
         HostClusters hc = build_clusters(src, cnt);
         const int ncl = (int)hc.lo.size();
         for (long long i = 0; i < n; ++i) {
@@ -124,7 +135,7 @@ void emul_knn_lbs(const float* part_pts, const float* part_pbw, const long long*
             nvr_knn_init(k);
             const float* p = pts + i * 3;
             if (!clustered) {
-                nvr_knn_scan(verts.data(), cnt, p, k);
+                for (int b = 0; b < nblk; ++b) nvr_knn_scan(verts.data() + (size_t)b * NVR_CL, p, k);
             } else if (ncl > 0) {
                 const float* rep = clustered == 2 ? p : pts + (i > 0 ? i - 1 : 0) * 3;   // 2: own point (best case)
                 int seed = 0;
@@ -133,12 +144,12 @@ void emul_knn_lbs(const float* part_pts, const float* part_pbw, const long long*
                     const float lb = nvr_aabb_lb(hc.lo[c], hc.hi[c], rep);
                     if (lb < best) { best = lb; seed = c; }
                 }
-                nvr_knn_scan(hc.verts.data() + (size_t)seed * NVR_CL, NVR_CL, p, k);
+                nvr_knn_scan(hc.verts.data() + (size_t)seed * NVR_CL, p, k);
                 ++scanned;
                 for (int c = 0; c < ncl; ++c) {
                     if (c == seed) continue;
                     const float lb = nvr_aabb_lb(hc.lo[c], hc.hi[c], p);
-                    if (!(lb * NVR_PRUNE_SLACK > nvr_knn_d2(k, 3))) { nvr_knn_scan(hc.verts.data() + (size_t)c * NVR_CL, NVR_CL, p, k); ++scanned; }
+                    if (!(lb * NVR_PRUNE_SLACK > nvr_knn_d2(k, 3))) { nvr_knn_scan(hc.verts.data() + (size_t)c * NVR_CL, p, k); ++scanned; }
                 }
             }
             float bw[NVR_JOINTS];
@@ -161,7 +172,9 @@ void emul_deformer(const NvrGrid* g, const NvrLinear* mlp, const float* tuv, int
     DeformerMlp m{mlp[0].weight, mlp[0].bias, mlp[1].weight, mlp[1].bias, mlp[2].weight, mlp[2].bias};
     VolumeDev v{tuv, D, H, W, 2, tbounds};
     float sc[32];
-    for (long long i = 0; i < n; ++i) nvr_deformer_point(d, m, v, frame_dim, x0 + i * 3, out + i * 3, sc, 1);
+    alignas(16) float pk[NVR_DEF_PACKED_FLOATS];                  // the layout stage_deformer builds in shared memory
+    nvr_pack_deformer(m, pk, 0, 1);
+    for (long long i = 0; i < n; ++i) nvr_deformer_point(d, pk, v, frame_dim, x0 + i * 3, out + i * 3, sc, 1);
 }
 
 void emul_posenc(const float* v, long long n, float* out) {

@@ -128,12 +128,14 @@ def test_part_mlp(gpu):
         assert err < 5e-6, (pid, err)
 
 
-def test_part_mlp_tensor_core(gpu):
-    """The tcgen05 3xTF32 MLP kernel against the fp32 oracle (and against our fp32 FFMA kernel)."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_part_mlp_tensor_core(gpu, mode):
+    """The tcgen05 3xTF32 MLP kernel (mode 1: one epilogue warpgroup per tile slot, mode 2: two) against the fp32
+    oracle (and against our fp32 FFMA kernel)."""
     from instant_nvr_b200.engine import Engine
     g = torch.Generator().manual_seed(14)
     net, sd, frame = gpu["nets"][200.0], gpu["sds"][200.0], gpu["frame"]
-    eng_tc = Engine(gpu["cfg"], mlp_mode=1)
+    eng_tc = Engine(gpu["cfg"], mlp_mode=mode)
     eng_tc.bind_params(net)
     eng_ff = Engine(gpu["cfg"], mlp_mode=0)
     eng_ff.bind_params(net)
@@ -152,7 +154,7 @@ def test_part_mlp_tensor_core(gpu):
             ref = torch.cat([rgb, occ], -1)
             err = (ours - ref).abs().max().item()
             err_ff = (ours - ffma).abs().max().item()
-            diag("part_mlp_tc", part=pid, n=n, max_err_vs_oracle=err, max_err_vs_ffma=err_ff)
+            diag("part_mlp_tc", mode=mode, part=pid, n=n, max_err_vs_oracle=err, max_err_vs_ffma=err_ff)
             assert err < 2e-5, (pid, n, err)          # north-star bound is 1e-4; the fp32 FFMA kernel holds 5e-6
 
 
