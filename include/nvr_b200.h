@@ -115,7 +115,12 @@ typedef struct NvrConfig {
     float smpl_thresh;             /* cfg.smpl_thresh */
     int32_t mlp_mode;              /* part MLPs: 0 fp32 FFMA tiles; 1 tcgen05 3xTF32 tiles, 256-thread CTAs; 2 the same with two
                                       epilogue warpgroups per tile slot (512-thread CTAs) */
+    uint32_t tune;                 /* NVR_TUNE_* bits: occupancy variants of the same kernels (identical results) */
+    uint32_t _pad;
 } NvrConfig;
+#define NVR_TUNE_WARP_OCC8 1u      /* k_warp compiled for 8 CTAs/SM (<= 64 registers) */
+#define NVR_TUNE_KNN_OCC5 2u       /* k_knn compiled for 5 CTAs/SM (<= 48 registers) */
+#define NVR_TUNE_NO_CULL_EARLY_OUT 4u  /* cull: always take the 8-tap lookup (disable the coarse-minimum early-out) */
 
 /* Device-side work counters of the most recent pass (diagnostics / benchmark accounting). */
 typedef struct NvrCounters {

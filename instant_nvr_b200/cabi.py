@@ -58,7 +58,8 @@ class NvrFrame(C.Structure):
 
 
 class NvrConfig(C.Structure):
-    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("smpl_thresh", C.c_float), ("mlp_mode", C.c_int32)]
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("smpl_thresh", C.c_float), ("mlp_mode", C.c_int32),
+                ("tune", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class NvrCounters(C.Structure):

@@ -30,7 +30,7 @@ struct NvrEngine {
     NvrFrame frame;
     FrameDev fdev;
     // per-frame device buffers owned by the engine (grow-only)
-    float* d_dist = nullptr; size_t dist_cap = 0;
+    float* d_dist = nullptr; size_t dist_cap = 0;        // compact distance volume, followed by its coarse minimum grid
     float4* d_verts = nullptr; size_t verts_cap = 0;      // clustered vertices + 2 AABB corners per cluster
     int* d_cl_off = nullptr;
     int* d_perm = nullptr; size_t perm_cap = 0;            // KD partition: cluster slot -> vertex index in its part
@@ -209,11 +209,12 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
     const size_t n_vox = (size_t)f->pbw_dims[0] * f->pbw_dims[1] * f->pbw_dims[2];
     const size_t max_cl = (size_t)NVR_NUM_PARTS * ((f->maxlen + NVR_CL - 1) / NVR_CL);
     const size_t n_verts = max_cl * NVR_CL + 2 * max_cl;   // float4 slots: vertices, then cl_lo, then cl_hi
-    if (n_vox > h->dist_cap) {
+    const size_t n_coarse = (size_t)nvr_coarse_dim(f->pbw_dims[0]) * nvr_coarse_dim(f->pbw_dims[1]) * nvr_coarse_dim(f->pbw_dims[2]);
+    if (n_vox + n_coarse > h->dist_cap) {
         NVR_CHECK(h, cudaFree(h->d_dist));
         h->d_dist = nullptr; h->dist_cap = 0;
-        NVR_CHECK(h, cudaMalloc(&h->d_dist, n_vox * sizeof(float)));
-        h->dist_cap = n_vox;
+        NVR_CHECK(h, cudaMalloc(&h->d_dist, (n_vox + n_coarse) * sizeof(float)));
+        h->dist_cap = n_vox + n_coarse;
     }
     if (n_verts > h->verts_cap) {
         NVR_CHECK(h, cudaFree(h->d_verts));
@@ -230,6 +231,10 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
     StageTimer tm_(h, stream, NVR_STAGE_PREP);
     k_frame_prep<<<std::min<int>(h->sm_count * 4, (int)((n_vox + 255) / 256)), 256, 0, stream>>>(
         f->pbw, (int)n_vox, f->pbw_channels, h->d_dist);
+    float* d_cmin = h->d_dist + n_vox;
+    k_frame_coarse<<<std::min<int>(h->sm_count * 4, (int)((n_coarse + 127) / 128)), 128, 0, stream>>>(
+        h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], d_cmin);
+    h->launches++;
     float4* cl_lo = h->d_verts + max_cl * NVR_CL;
     float4* cl_hi = cl_lo + max_cl;
     if (f->topology_key == 0 || f->topology_key != h->perm_key || f->maxlen != h->perm_maxlen) {
@@ -246,6 +251,7 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
     FrameDev& d = h->fdev;
     d.R = f->R; d.Th = f->Th;
     d.dist = VolumeDev{h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], 1, f->pbounds};
+    d.dist_cmin = (h->cfg.tune & NVR_TUNE_NO_CULL_EARLY_OUT) ? nullptr : d_cmin;
     d.tuv = VolumeDev{f->tuv, f->tuv_dims[0], f->tuv_dims[1], f->tuv_dims[2], 2, f->tbounds};
     d.verts = h->d_verts; d.cl_lo = cl_lo; d.cl_hi = cl_hi; d.cl_off = h->d_cl_off; d.part_pbw = f->part_pbw; d.maxlen = f->maxlen;
     d.A = f->A; d.bigA = f->big_A; d.frame_dim = f->frame_dim; d.latent_index = (const long long*)f->latent_index;
@@ -317,10 +323,16 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     // neighbour records alias the embedding buffer: they are consumed by k_warp before k_embed writes it
     KnnRec* recs = (KnnRec*)w.emb;
     { StageTimer t(h, st, NVR_STAGE_KNN);
-    k_knn<<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg); }
+    if (h->cfg.tune & NVR_TUNE_KNN_OCC5)        // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
+        k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg);
+    else
+        k_knn<1><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg); }
     { StageTimer t(h, st, NVR_STAGE_WARP);
-    k_warp<<<dim3(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS), WARP_THREADS, 0, st>>>(
-        h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd); }
+    const dim3 wg(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS);
+    if (h->cfg.tune & NVR_TUNE_WARP_OCC8)       // <= 64 registers: 8 CTAs (32 warps) per SM instead of 6
+        k_warp<8><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd);
+    else
+        k_warp<1><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd); }
     const bool tc = h->cfg.mlp_mode >= 1;
     if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
         StageTimer t(h, st, NVR_STAGE_MLP);

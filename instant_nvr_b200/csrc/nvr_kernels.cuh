@@ -34,6 +34,7 @@ struct FrameDev {                  // per-frame tensors as the kernels see them
     const float* R;
     const float* Th;
     VolumeDev dist;                // compact (D,H,W,1) distance volume
+    const float* dist_cmin;        // per coarse cell minimum of dist (nvr_cull_early_out); null = no early-out
     VolumeDev tuv;                 // (D',H',W',2)
     const float4* verts;           // part vertices, spatially sorted: one 16-float4 SoA block per cluster (x | y | z | orig index)
     const float4* cl_lo;           // per-cluster AABB
@@ -62,6 +63,13 @@ struct PartMlpDev {
 __global__ void k_frame_prep(const float* __restrict__ pbw, int n_vox, int C, float* __restrict__ dist) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int i = tid; i < n_vox; i += nth) dist[i] = pbw[(long long)i * C + (C - 1)];
+}
+
+// coarse minimum grid of the compact distance volume (one thread per coarse cell, 125 voxels each)
+__global__ void k_frame_coarse(const float* __restrict__ dist, int D, int H, int W, float* __restrict__ cmin) {
+    const int cD = nvr_coarse_dim(D), cH = nvr_coarse_dim(H), cW = nvr_coarse_dim(W);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cD * cH * cW; i += gridDim.x * blockDim.x)
+        cmin[i] = nvr_coarse_min(dist, D, H, W, i / (cH * cW), (i / cW) % cH, i % cW);
 }
 
 // Per-frame KNN acceleration structure, one CTA per part: a balanced KD partition of the part's posed
@@ -313,9 +321,13 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
                 w[0] = pts[i * 3]; w[1] = pts[i * 3 + 1]; w[2] = pts[i * 3 + 2];
             }
             nvr_world_to_pose(fr.R, fr.Th, w, p);
-            float pn;
-            nvr_sample_volume(fr.dist, p, 0, 1, &pn);
-            keep = pn < thresh;                                   // inb_part_network_multiassign.py:136
+            float c[3];
+            nvr_volume_coords(fr.dist, p, c);
+            if (!(fr.dist_cmin && nvr_cull_early_out(fr.dist, fr.dist_cmin, c, thresh))) {
+                float pn;
+                nvr_sample_volume_at(fr.dist, c, 0, 1, &pn);
+                keep = pn < thresh;                               // inb_part_network_multiassign.py:136
+            }
         }
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) warp_cnt[wid] = __popc(ballot);
@@ -349,7 +361,8 @@ struct __align__(16) KnnRec {      // a flagged (sample, part) pair before the w
     int _pad[3];
 };
 
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_knn(FrameDev fr, float thresh, int* __restrict__ counters, const float4* __restrict__ surv,
       KnnRec* __restrict__ recs, int cap, float4* __restrict__ raws, float* __restrict__ dbg) {
     // dbg (optional, per SAMPLE): [n][5][8] = flag, x, y, z, vx, vy, vz, pdist -- per-stage parity tests
@@ -425,7 +438,8 @@ __device__ __forceinline__ DeformerSmem stage_deformer(float* sm, const Deformer
     return d;
 }
 
-__global__ void __launch_bounds__(WARP_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(WARP_THREADS, MINB)
 k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs, int dir_div,
        const int* __restrict__ counters, const float4* __restrict__ surv, const KnnRec* __restrict__ recs,
        PairRec* __restrict__ pairs, int cap, float* __restrict__ dbg, float* __restrict__ out_x0, float* __restrict__ out_resd) {

@@ -237,9 +237,9 @@ NVR_HD void nvr_embed_point(const GridDev& g, const float x[3], float* out, int 
 //                                                     blend_utils.py:501-525, 528-555
 // ---------------------------------------------------------------------------------------
 // channels [ch0, ch0+nch) of the C-channel volume; point axis x->D, y->H, z->W.
-NVR_HD void nvr_sample_volume(const VolumeDev& v, const float p[3], int ch0, int nch, float* out) {
+// clipped continuous voxel coordinates of p along the volume's (D, H, W) axes
+NVR_HD void nvr_volume_coords(const VolumeDev& v, const float p[3], float c[3]) {
     const int dims[3] = {v.D, v.H, v.W};
-    float c[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         float g = (p[a] - v.bounds[a]) / (v.bounds[3 + a] - v.bounds[a]);
@@ -248,6 +248,14 @@ NVR_HD void nvr_sample_volume(const VolumeDev& v, const float p[3], int ch0, int
         t = fminf(fmaxf(t, 0.0f), (float)(dims[a] - 1));          // clip_coordinates (border)
         c[a] = t;
     }
+}
+NVR_HD void nvr_sample_volume_at(const VolumeDev& v, const float c[3], int ch0, int nch, float* out);
+NVR_HD void nvr_sample_volume(const VolumeDev& v, const float p[3], int ch0, int nch, float* out) {
+    float c[3];
+    nvr_volume_coords(v, p, c);
+    nvr_sample_volume_at(v, c, ch0, nch, out);
+}
+NVR_HD void nvr_sample_volume_at(const VolumeDev& v, const float c[3], int ch0, int nch, float* out) {
     // ATen names: x <-> W (our z), y <-> H (our y), z <-> D (our x)
     const float ix = c[2], iy = c[1], iz = c[0];
     const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
@@ -266,6 +274,31 @@ NVR_HD void nvr_sample_volume(const VolumeDev& v, const float p[3], int ch0, int
             for (int k = 0; k < nch; ++k) out[k] += src[k] * w;
         }
     }
+}
+
+// Conservative early-out for the distance cull.  A trilinear lookup is a convex combination of the 8 voxels around
+// (floor(c), floor(c) + 1), so it cannot fall below their minimum.  cmin holds, per coarse cell of NVR_CULL_B^3 fine
+// cells, the minimum of the distance volume over fine indices [cB, cB + B] per axis (one past the cell, for the +1
+// corners).  If that minimum exceeds the threshold by more than the rounding of the 8-term sum, the sample is culled
+// without touching the fine volume; everything else takes the exact path, so the survivor set is unchanged.
+#define NVR_CULL_B 4
+#define NVR_CULL_MARGIN 1.00001f
+NVR_HD int nvr_coarse_dim(int d) { return (d + NVR_CULL_B - 1) / NVR_CULL_B; }
+NVR_HD bool nvr_cull_early_out(const VolumeDev& v, const float* cmin, const float c[3], float thresh) {
+    const int cz = (int)floorf(c[0]) / NVR_CULL_B, cy = (int)floorf(c[1]) / NVR_CULL_B, cx = (int)floorf(c[2]) / NVR_CULL_B;
+    const float m = cmin[((long long)cz * nvr_coarse_dim(v.H) + cy) * nvr_coarse_dim(v.W) + cx];
+    return m > thresh * NVR_CULL_MARGIN;
+}
+// minimum of a 1-channel volume over the fine indices a coarse cell's lookups can touch
+NVR_HD float nvr_coarse_min(const float* dist, int D, int H, int W, int cz, int cy, int cx) {
+    float m = INFINITY;
+    for (int z = cz * NVR_CULL_B; z <= cz * NVR_CULL_B + NVR_CULL_B && z < D; ++z)
+        for (int y = cy * NVR_CULL_B; y <= cy * NVR_CULL_B + NVR_CULL_B && y < H; ++y)
+            for (int x = cx * NVR_CULL_B; x <= cx * NVR_CULL_B + NVR_CULL_B && x < W; ++x) {
+                const float d = dist[((long long)z * H + y) * W + x];
+                m = (d < m || d != d) ? d : m;                  // a NaN voxel poisons the cell: never early-out on it
+            }
+    return m;
 }
 
 // ---------------------------------------------------------------------------------------

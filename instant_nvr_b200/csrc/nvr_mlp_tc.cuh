@@ -337,6 +337,10 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
             tc_fence_after();
             gemm3_ss(tbase + TC_COL_HHI, s_xhi, s_xlo, s_p0, TC_K0, TC_K0, idesc, true);
             umma_commit(bar_a);
+            // the x half of GEMM 2 needs nothing from the first epilogue: queue it now (D is free: the previous
+            // tile's last reads were fenced before the slot barrier above) so it runs under that epilogue;
+            // it is covered by GEMM 2's commit below, not by the one just issued
+            gemm3_ss(tbase + TC_COL_D, s_xhi, s_xlo, s_px, TC_KX, TC_KX, idesc, true);
         }
         mbar_wait(bar_a, phase); phase ^= 1;
         tc_fence_after();
@@ -359,10 +363,9 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
         slot_sync<H>(slot);
         if (H == 2 && lead) o0 += ex[0];
         const float occ = 1.0f - expf(-nvr_softplus(o0));           // :51 (used by the lead half only)
-        // ---- GEMM 2: g_pre = W2x x + M h
+        // ---- GEMM 2: g_pre = W2x x (queued with GEMM 0) + M h
         if (stid == 0 && lead) {
             tc_fence_after();
-            gemm3_ss(tbase + TC_COL_D, s_xhi, s_xlo, s_px, TC_KX, TC_KX, idesc, true);
             gemm3_ts(tbase + TC_COL_D, tbase + TC_COL_HHI, tbase + TC_COL_HLO, s_pm, TC_KH, idesc, false);
             umma_commit(bar_a);
         }

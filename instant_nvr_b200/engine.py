@@ -30,6 +30,7 @@ def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
 
 
 DEFAULT_MLP_MODE = 1
+DEFAULT_TUNE = 0
 
 
 def _params_struct(net, grads: Optional[Dict[str, torch.Tensor]] = None) -> "cabi.NvrParams":
@@ -85,7 +86,8 @@ class Engine:
         self.lib = cabi.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.max_points_per_pass = int(os.environ.get("NVR_PASS_POINTS", max_points_per_pass))
-        conf = cabi.NvrConfig(cabi.ABI_VERSION, self.device.index or 0, float(cfg.smpl_thresh), int(mlp_mode))
+        self.tune = int(os.environ.get("NVR_TUNE", DEFAULT_TUNE))      # NVR_TUNE_* bits of include/nvr_b200.h
+        conf = cabi.NvrConfig(cabi.ABI_VERSION, self.device.index or 0, float(cfg.smpl_thresh), int(mlp_mode), self.tune, 0)
         h = C.c_void_p()
         rc = self.lib.nvr_create(C.byref(conf), C.byref(h))
         if rc != 0 or not h.value:

@@ -230,4 +230,20 @@ void emul_adam(float* p, const float* g, float* m, float* v, long long n, long l
     s.bc2_sqrt = (float)sqrt(bc2);
     for (long long i = 0; i < n; ++i) nvr_adam_update(s, p[i], g[i], m[i], v[i]);
 }
+// distance cull with and without the coarse-minimum early-out (k_frame_coarse + k_cull): keep[i] = exact decision,
+// early[i] = 1 when the early-out fires (it must then agree with a culled exact decision).
+void emul_cull(const float* dist, int D, int H, int W, const float* bounds, const float* pts, long long n, float thresh,
+               unsigned char* keep, unsigned char* early) {
+    VolumeDev v{dist, D, H, W, 1, bounds};
+    const int cD = nvr_coarse_dim(D), cH = nvr_coarse_dim(H), cW = nvr_coarse_dim(W);
+    std::vector<float> cmin((size_t)cD * cH * cW);
+    for (int i = 0; i < cD * cH * cW; ++i) cmin[i] = nvr_coarse_min(dist, D, H, W, i / (cH * cW), (i / cW) % cH, i % cW);
+    for (long long i = 0; i < n; ++i) {
+        float c[3], pn;
+        nvr_volume_coords(v, pts + i * 3, c);
+        early[i] = nvr_cull_early_out(v, cmin.data(), c, thresh) ? 1 : 0;
+        nvr_sample_volume_at(v, c, 0, 1, &pn);
+        keep[i] = pn < thresh ? 1 : 0;
+    }
+}
 }

@@ -60,12 +60,13 @@ def test_fused_adam_matches_torch_adam(wd):
             assert torch.all((so["exp_avg_sq"] - sr["exp_avg_sq"]).abs() <= 2e-6 * sr["exp_avg_sq"].abs() + 4e-10 * gm ** 2), i
             torch.testing.assert_close(q.detach(), p.detach(), rtol=1.2e-7, atol=4e-9)
     # checkpoints interchange: continue the fused run in torch.optim.Adam and vice versa
-    sd = o_our.state_dict()
+    import copy
+    sd = copy.deepcopy(o_our.state_dict())               # load_state_dict may alias tensors that already fit
     cont = [torch.nn.Parameter(q.detach().clone()) for q in ours]
     o_cont = torch.optim.Adam(groups(cont), lr=5e-4, eps=1e-15, weight_decay=wd)
     o_cont.load_state_dict(sd)
     o_back = FusedAdam(groups([torch.nn.Parameter(p.detach().clone()) for p in ref]), lr=5e-4, eps=1e-15, weight_decay=wd)
-    o_back.load_state_dict(o_ref.state_dict())
+    o_back.load_state_dict(copy.deepcopy(o_ref.state_dict()))
     gs = _grads(init, 9)
     back = [p for g in o_back.param_groups for p in g["params"]]
     for p, q, r, g in zip(ref, cont, back, gs):

@@ -244,3 +244,32 @@ def test_posenc_and_activations(emul):
     emul.emul_activations(fp(x), C.c_longlong(x.numel()), fp(sp), fp(sg))
     assert torch.allclose(sp, torch.nn.functional.softplus(x), rtol=2e-6, atol=1e-30)
     assert torch.allclose(sg, torch.sigmoid(x), rtol=2e-6, atol=1e-30)
+
+
+def test_cull_early_out_is_conservative(emul):
+    """The coarse-minimum early-out of k_cull may only fire on samples the exact 8-tap lookup culls too; on the synthetic
+    frame it should remove most of the work (samples far from the body)."""
+    from instant_nvr_b200.synthetic import make_frame
+    frame = make_frame(seed=3)
+    dist = frame["pbw"][0, ..., -1].contiguous()
+    D, H, W = dist.shape
+    b = frame["pbounds"][0].contiguous()
+    g = torch.Generator().manual_seed(0)
+    lo, hi = b[0], b[1]
+    pts = (lo + (hi - lo) * (torch.rand(400000, 3, generator=g) * 1.3 - 0.15)).contiguous()     # inside and outside the bbox
+    special = torch.tensor([[float("nan"), 0.0, 0.0], [float("inf"), 0.0, 0.0], [-float("inf"), 1.0, 1.0]])
+    pts = torch.cat([pts, special, lo[None], hi[None]]).contiguous()
+    n = pts.shape[0]
+    for thresh in (0.05, 0.1):
+        keep, early = torch.zeros(n, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8)
+        emul.emul_cull(fp(dist), C.c_int(D), C.c_int(H), C.c_int(W), fp(b), fp(pts), C.c_longlong(n), C.c_float(thresh),
+                       fp(keep), fp(early))
+        assert not (early.bool() & keep.bool()).any()
+        culled = ~keep.bool()
+        assert keep.sum() > 1000
+        assert early.sum() > 0.6 * culled.sum(), (int(early.sum()), int(culled.sum()))
+    # adversarial volume: values straddling the threshold by a few ulps everywhere
+    vol = (0.05 * (1.0 + 3e-6 * torch.randn(D, H, W, generator=g))).contiguous()
+    keep, early = torch.zeros(n, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8)
+    emul.emul_cull(fp(vol), C.c_int(D), C.c_int(H), C.c_int(W), fp(b), fp(pts), C.c_longlong(n), C.c_float(0.05), fp(keep), fp(early))
+    assert not (early.bool() & keep.bool()).any() and keep.any()
