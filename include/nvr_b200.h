@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 6
+#define NVR_ABI_VERSION 7
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -274,6 +274,52 @@ int nvr_generate_rays(NvrHandle h, int32_t H, int32_t W, const double* K_inv_hos
  * by n and takes -10 log10 for the PSNR).  sq_sum is a device double, overwritten. */
 int nvr_assemble_image(NvrHandle h, const float* rgb, const int32_t* coord, int64_t n_rays, int64_t n_pixels, float* img, void* stream);
 int nvr_sq_diff_sum(NvrHandle h, const float* a, const float* b, int64_t n, double* sq_sum, void* stream);
+
+/* -- Per-frame SMPL preprocessing (8(f) rank 3): what the reference's dataset computes in numpy for every frame
+ * (lib/datasets/h36m/tpose_dataset.py:247-293 prepare_input, :570-600 part tables; get_rigid_transformation,
+ * lib/utils/if_nerf/if_nerf_data_utils.py:523-577; get_bounds :689-696) and what its offline tool pre-bakes to
+ * lbs/bweights/{frame}.npy (tools/prepare_zjumocap.py:474-508 get_bweights, :152-165 get_grid_points), on the device, so a
+ * frame goes from (pose parameters, world vertices) to a bound NvrFrame without touching the host or the disk.
+ *
+ * NvrSmplPose is HOST data (the numbers of one new_params/{frame}.npy + the subject's joints / parents); they travel as
+ * kernel parameters.  poses / big_poses are axis-angles (24,3); joints is lbs/joints.npy as float32 (the reference does
+ * the parent-relative subtraction in float32, :554-555); parents[0] is ignored.
+ * Device inputs: wxyz (V,3) fp32 world vertices (new_vertices/{frame}.npy); vert_slot (V) int32 = part * maxlen + rank of
+ * the vertex inside its part (static per subject; -1 = in no part) -- may be NULL together with part_pts.
+ * Device outputs (any may be NULL): R (3,3), Th (3), A / big_A (24,4,4), ppts (V,3), part_pts (P,maxlen,3) -- rows
+ * beyond a part's length are NOT written (zero them once), pbounds / wbounds (2,3) = bbox(ppts / wxyz) -+ box_padding.
+ * The workspace (nvr_smpl_workspace_bytes(V) bytes, 256-byte aligned) also keeps the float64 posed vertices the volume is
+ * built from; pass the same one to the two calls below.
+ *
+ * nvr_smpl_volume_dims SYNCHRONISES the stream: it reads the float64 bbox back and returns the volume's dims
+ * (D,H,W) = lengths of np.arange(min - 0.05, max + 0.05 + 0.025, 0.025) per axis and their first elements origin[3].
+ * nvr_smpl_bweights fills pbw (D,H,W,25) fp32: the 24 skinning weights (`weights` (V,24), device) of the posed vertex
+ * nearest to each voxel centre and the distance to it, both from float64 arithmetic (psbody closest_vertices(use_cgal=True)
+ * = exact nearest vertex; lowest index on exact ties). */
+typedef struct NvrSmplPose {
+    double Rh[3];
+    double Th[3];
+    double poses[72];
+    double big_poses[72];
+    float joints[72];
+    int32_t parents[24];
+} NvrSmplPose;
+typedef struct NvrSmplOut {
+    float* R;
+    float* Th;
+    float* A;
+    float* big_A;
+    float* ppts;
+    float* part_pts;
+    float* pbounds;
+    float* wbounds;
+} NvrSmplOut;
+size_t nvr_smpl_workspace_bytes(int32_t n_verts);
+int nvr_smpl_pose_frame(NvrHandle h, const NvrSmplPose* pose_host, const float* wxyz, int32_t n_verts, const int32_t* vert_slot,
+                        int32_t maxlen, float box_padding, const NvrSmplOut* out, void* workspace, size_t ws_bytes, void* stream);
+int nvr_smpl_volume_dims(NvrHandle h, const void* workspace, int32_t dims[3], double origin[3], void* stream);
+int nvr_smpl_bweights(NvrHandle h, const void* workspace, int32_t n_verts, const float* weights, const int32_t dims[3],
+                      const double origin[3], float* pbw, void* stream);
 
 /* Per-stage device timing.  nvr_profile(h, 1) clears the accumulators and makes every later launch
  * record a CUDA-event pair on its stream; nvr_profile_read synchronises the device and sums them. */

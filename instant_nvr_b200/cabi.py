@@ -12,7 +12,7 @@ from typing import Optional
 
 MAX_LEVELS = 16
 NUM_PARTS = 5
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnvr_b200.so")
@@ -77,6 +77,16 @@ class NvrAdamTensor(C.Structure):
                 ("numel", C.c_int64), ("step", C.c_int64), ("lr", C.c_double), ("weight_decay", C.c_double)]
 
 
+class NvrSmplPose(C.Structure):
+    _fields_ = [("Rh", C.c_double * 3), ("Th", C.c_double * 3), ("poses", C.c_double * 72), ("big_poses", C.c_double * 72),
+                ("joints", C.c_float * 72), ("parents", C.c_int32 * 24)]
+
+
+class NvrSmplOut(C.Structure):
+    _fields_ = [("R", C.c_void_p), ("Th", C.c_void_p), ("A", C.c_void_p), ("big_A", C.c_void_p), ("ppts", C.c_void_p),
+                ("part_pts", C.c_void_p), ("pbounds", C.c_void_p), ("wbounds", C.c_void_p)]
+
+
 STAGE_NAMES = ("prep", "cull", "knn", "warp", "embed", "mlp", "resolve")
 
 # name -> (restype, argtypes); exactly the declarations of include/nvr_b200.h
@@ -118,6 +128,12 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nvr_assemble_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "nvr_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nvr_smpl_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "nvr_smpl_pose_frame": (C.c_int, [C.c_void_p, C.POINTER(NvrSmplPose), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
+                                      C.POINTER(NvrSmplOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nvr_smpl_volume_dims": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p]),
+    "nvr_smpl_bweights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                    C.c_void_p, C.c_void_p]),
     "nvr_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "nvr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(NvrStageProfile)]),
     "nvr_read_counters": (C.c_int, [C.c_void_p, C.POINTER(NvrCounters), C.c_void_p]),

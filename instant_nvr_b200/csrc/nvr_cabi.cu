@@ -13,6 +13,7 @@
 
 #include "../../include/nvr_b200.h"
 #include "nvr_kernels.cuh"
+#include "nvr_smpl.cuh"
 #include "nvr_mlp_tc.cuh"
 #include "nvr_train.cuh"
 #include "nvr_aux.cuh"
@@ -781,6 +782,71 @@ extern "C" int nvr_sq_diff_sum(NvrHandle h, const float* a, const float* b, int6
     NVR_CHECK(h, cudaMemsetAsync(sq_sum, 0, sizeof(double), st));
     if (n == 0) return 0;
     k_sq_diff<<<grid_for(n, 256 * 8, h->sm_count * 8), 256, 0, st>>>(a, b, n, sq_sum);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+// ---- per-frame SMPL preprocessing ---------------------------------------------------------
+extern "C" size_t nvr_smpl_workspace_bytes(int32_t n_verts) {
+    return n_verts < 0 ? 0 : (size_t)SMPL_WS_PXYZ + (size_t)n_verts * 3 * sizeof(double);
+}
+
+extern "C" int nvr_smpl_pose_frame(NvrHandle h, const NvrSmplPose* pose, const float* wxyz, int32_t n_verts, const int32_t* vert_slot,
+                                   int32_t maxlen, float box_padding, const NvrSmplOut* out, void* workspace, size_t ws_bytes,
+                                   void* stream_) {
+    if (!h) return 1;
+    if (!pose || !wxyz || !out || n_verts < 1) return fail(h, "nvr_smpl_pose_frame: null argument / no vertices");
+    if (!out->R || !out->Th || !out->ppts) return fail(h, "nvr_smpl_pose_frame: R, Th and ppts outputs are required");
+    if ((vert_slot != nullptr) != (out->part_pts != nullptr) || (vert_slot && maxlen < 1))
+        return fail(h, "nvr_smpl_pose_frame: vert_slot, maxlen and part_pts go together");
+    if (!workspace || ((uintptr_t)workspace & 255) || ws_bytes < nvr_smpl_workspace_bytes(n_verts))
+        return fail(h, "nvr_smpl_pose_frame: workspace too small or not 256-byte aligned (nvr_smpl_workspace_bytes)");
+    for (int j = 1; j < NVR_JOINTS; ++j)
+        if (pose->parents[j] < 0 || pose->parents[j] >= j) return fail(h, "nvr_smpl_pose_frame: parents must precede their children");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    static_assert(sizeof(SmplPoseDev) == sizeof(NvrSmplPose), "SmplPoseDev mirrors NvrSmplPose");
+    SmplPoseDev P;
+    memcpy(&P, pose, sizeof(P));
+    P.parents[0] = 0;
+    cudaStream_t st = (cudaStream_t)stream_;
+    unsigned char* ws = (unsigned char*)workspace;
+    k_smpl_transforms<<<1, 64, 0, st>>>(P, out->A, out->big_A, out->R, out->Th, ws);
+    k_smpl_pose_verts<<<(n_verts + 255) / 256, 256, 0, st>>>(wxyz, n_verts, out->R, out->Th, vert_slot, out->ppts, out->part_pts, ws);
+    k_smpl_bounds<<<1, 32, 0, st>>>(ws, box_padding, out->pbounds, out->wbounds);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches += 3;
+    return 0;
+}
+
+extern "C" int nvr_smpl_volume_dims(NvrHandle h, const void* workspace, int32_t dims[3], double origin[3], void* stream_) {
+    if (!h) return 1;
+    if (!workspace || !dims || !origin) return fail(h, "nvr_smpl_volume_dims: null argument");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    unsigned long long box[6];
+    cudaStream_t st = (cudaStream_t)stream_;
+    NVR_CHECK(h, cudaMemcpyAsync(box, (const unsigned char*)workspace + SMPL_WS_F64BOX, sizeof(box), cudaMemcpyDeviceToHost, st));
+    NVR_CHECK(h, cudaStreamSynchronize(st));
+    for (int a = 0; a < 3; ++a) {
+        // get_grid_points (tools/prepare_zjumocap.py:152-165): min -= 0.05, max += 0.05, arange(min, max + vsize, vsize)
+        const double lo = unord64(box[a]) - 0.05, hi = unord64(box[3 + a]) + 0.05;
+        if (!(lo <= hi)) return fail(h, "nvr_smpl_volume_dims: empty / non-finite vertex bbox (run nvr_smpl_pose_frame first)");
+        origin[a] = lo;
+        dims[a] = nvr_arange_len(lo, hi + 0.025, 0.025);
+    }
+    return 0;
+}
+
+extern "C" int nvr_smpl_bweights(NvrHandle h, const void* workspace, int32_t n_verts, const float* weights, const int32_t dims[3],
+                                 const double origin[3], float* pbw, void* stream_) {
+    if (!h) return 1;
+    if (!workspace || !weights || !dims || !origin || !pbw || n_verts < 1) return fail(h, "nvr_smpl_bweights: null argument");
+    const long long n_vox = (long long)dims[0] * dims[1] * dims[2];
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || n_vox > (1ll << 28)) return fail(h, "nvr_smpl_bweights: bad volume dims");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream_;
+    k_smpl_bweights<<<(unsigned)((n_vox + 255) / 256), 256, 0, st>>>((const unsigned char*)workspace, n_verts, weights, dims[0], dims[1],
+                                                                     dims[2], origin[0], origin[1], origin[2], 0.025, pbw);
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return 0;

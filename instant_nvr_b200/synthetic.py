@@ -120,10 +120,9 @@ def _lbs(W: np.ndarray, A: np.ndarray, V: np.ndarray) -> np.ndarray:
     return np.einsum("vab,vb->va", M[:, :3, :3], V) + M[:, :3, 3]
 
 
-def make_frame(seed: int = 0, n_verts: int = 6890, pose_scale: float = 0.2, voxel: float = 0.025,
-               latent_index: int = 25, num_train_frame: int = 100) -> Dict[str, torch.Tensor]:
-    """One reference-style per-frame ``batch`` (without rays).  All tensors CPU, batch dim 1."""
-    rng = np.random.default_rng(seed)
+def _subject(rng: np.random.Generator, n_verts: int, pose_scale: float) -> Dict[str, np.ndarray]:
+    """The pseudo-SMPL subject and its pose: everything the reference reads from ``lbs/*.npy``, ``smpl-meta/*.npy``,
+    ``new_params/{i}.npy`` and ``new_vertices/{i}.npy`` (float64; callers cast)."""
     # ---- T-pose vertices on capsules, count proportional to surface area -------------------
     areas = np.array([2 * np.pi * r * np.linalg.norm(_J[b] - _J[a]) + 4 * np.pi * r * r for a, b, r in _BONES])
     counts = np.floor(areas / areas.sum() * n_verts).astype(int)
@@ -156,6 +155,30 @@ def make_frame(seed: int = 0, n_verts: int = 6890, pose_scale: float = 0.2, voxe
     R = _rodrigues(Rh)
     Th = np.array([[0.12, 0.04, -0.2]])
     V_world = V_pose @ R.T + Th                      # blend_utils.py:385-392 (inverse of world->pose)
+    return {"V_T": V_T, "W": W, "parts": parts, "big_poses": big_poses, "big_A": big_A, "poses": poses, "A": A,
+            "V_big": V_big, "V_pose": V_pose, "Rh": Rh, "R": R, "Th": Th, "V_world": V_world}
+
+
+def make_subject(seed: int = 0, n_verts: int = 6890, pose_scale: float = 0.2) -> Dict[str, np.ndarray]:
+    """The raw per-subject / per-frame SMPL arrays of ``make_frame(seed)`` in the dtypes the reference's dataset loads
+    them with (``tpose_dataset.py:83-110, 247-265, 363-366``): what the frame preprocessing step (SURVEY.md 8(f)
+    rank 3, ``instant_nvr_b200.smpl_frame``) starts from."""
+    s = _subject(np.random.default_rng(seed), n_verts, pose_scale)
+    return {
+        "joints": _J.astype(np.float32), "parents": np.array([0] + PARENTS[1:], dtype=np.int64),
+        "weights": s["W"].astype(np.float32), "tpose": s["V_big"].astype(np.float32),
+        "wxyz": s["V_world"].astype(np.float32), "Rh": s["Rh"].astype(np.float32)[None], "Th": s["Th"].astype(np.float32),
+        "poses": s["poses"].astype(np.float32).reshape(-1), "big_poses": s["big_poses"].astype(np.float32),
+    }
+
+
+def make_frame(seed: int = 0, n_verts: int = 6890, pose_scale: float = 0.2, voxel: float = 0.025,
+               latent_index: int = 25, num_train_frame: int = 100) -> Dict[str, torch.Tensor]:
+    """One reference-style per-frame ``batch`` (without rays).  All tensors CPU, batch dim 1."""
+    rng = np.random.default_rng(seed)
+    s = _subject(rng, n_verts, pose_scale)
+    W, parts, A, big_A = s["W"], s["parts"], s["A"], s["big_A"]
+    V_big, V_pose, V_world, R, Th = s["V_big"], s["V_pose"], s["V_world"], s["R"], s["Th"]
 
     def bounds_of(x, pad):
         return np.stack([x.min(0) - pad, x.max(0) + pad]).astype(np.float32)

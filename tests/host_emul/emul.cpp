@@ -10,6 +10,7 @@
 
 #include "../../include/nvr_b200.h"
 #include "../../instant_nvr_b200/csrc/nvr_math.cuh"
+#include "../../instant_nvr_b200/csrc/nvr_smpl.cuh"
 
 static GridDev to_dev(const NvrGrid& g) {
     GridDev d;
@@ -196,8 +197,21 @@ int emul_sizeof(int which) {
         case 6: return (int)sizeof(NvrCounters);
         case 7: return (int)sizeof(NvrStageProfile);
         case 8: return (int)sizeof(NvrAdamTensor);
+        case 9: return (int)sizeof(NvrSmplPose);
+        case 10: return (int)sizeof(NvrSmplOut);
+        case 11: return (int)sizeof(SmplPoseDev);
     }
     return -1;
+}
+// per-frame SMPL preprocessing arithmetic (csrc/nvr_smpl.cuh)
+void emul_smpl_chain(const double* poses, const float* joints, const int* parents, float* out) {
+    double G[NVR_JOINTS * 16];
+    nvr_smpl_chain(poses, joints, parents, G, out);
+}
+void emul_rodrigues_cv(const double* r, double* R) { nvr_rodrigues_cv(r, R); }
+int emul_arange_len(double start, double stop, double step) { return nvr_arange_len(start, stop, step); }
+void emul_arange_fill(double start, double step, int n, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = nvr_arange_val(start, step, i);
 }
 // get_rays + get_near_far per pixel, row-major, no compaction (the kernels k_rays_mask / k_rays_emit run exactly
 // these two calls per pixel); o = float32 camera origin.

@@ -27,7 +27,8 @@ EMUL_DIR = os.path.join(REPO, "tests", "host_emul")
 def build_emul():
     so = os.path.join(EMUL_DIR, "libnvr_emul.so")
     src = os.path.join(EMUL_DIR, "emul.cpp")
-    deps = [src, os.path.join(REPO, "instant_nvr_b200", "csrc", "nvr_math.cuh"), os.path.join(REPO, "include", "nvr_b200.h")]
+    deps = [src, os.path.join(REPO, "instant_nvr_b200", "csrc", "nvr_math.cuh"), os.path.join(REPO, "instant_nvr_b200", "csrc", "nvr_smpl.cuh"),
+            os.path.join(REPO, "include", "nvr_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
     return C.CDLL(so)
@@ -44,7 +45,8 @@ def fp(t):
 
 def test_struct_sizes_match_header(emul):
     for which, cls in enumerate((cabi.NvrGrid, cabi.NvrLinear, cabi.NvrPart, cabi.NvrParams, cabi.NvrFrame,
-                                 cabi.NvrConfig, cabi.NvrCounters, cabi.NvrStageProfile, cabi.NvrAdamTensor)):
+                                 cabi.NvrConfig, cabi.NvrCounters, cabi.NvrStageProfile, cabi.NvrAdamTensor, cabi.NvrSmplPose,
+                                 cabi.NvrSmplOut, cabi.NvrSmplPose)):
         assert emul.emul_sizeof(which) == C.sizeof(cls), cls.__name__
 
 
