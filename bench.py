@@ -487,7 +487,12 @@ def main():
                        "l2": "no flush: each step streams 1.14 GB of tables + ~GBs of workspace, far above the 126 MB L2",
                        "survivor_fraction": per_step(prof["survivors"]) / (n_local * N_SAMPLES),
                        "active_pairs_per_sample": per_step(pairs) / (n_local * N_SAMPLES),
-                       "pairs_per_step_per_part": [per_step(p) for p in prof["pairs"]]},
+                       "pairs_per_step_per_part": [per_step(p) for p in prof["pairs"]],
+                       "far_pairs_per_step_per_part": [per_step(p) for p in prof.get("far_pairs", [0] * 5)],
+                       "pairs_note": "pairs = (sample, part) pairs evaluated (gather + MLPs); far pairs = flagged pairs of parts "
+                                     "farther than ~0.73 m (Gaussian weights sum < 1e-20), all answered by ONE shared evaluation per "
+                                     "part (NVR_TUNE=8 evaluates each on its own; results agree to fp32 rounding, "
+                                     "tests/test_gpu_parity.py::test_far_field_pairs_share_one_evaluation)"},
             "e2e": {"value": e2e_value, "unit": "ray-samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": n_local * 32 * world, "d2h_bytes_per_step": (n_local * 16 if world == 1 else n_total * 16 * world),
                     "api": "nvr_render_rays_host (pinned host rays -> H2D -> render -> D2H rgb/acc)" if world == 1 else

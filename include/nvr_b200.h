@@ -121,12 +121,17 @@ typedef struct NvrConfig {
 #define NVR_TUNE_WARP_OCC8 1u      /* k_warp compiled for 8 CTAs/SM (<= 64 registers) */
 #define NVR_TUNE_KNN_OCC5 2u       /* k_knn compiled for 5 CTAs/SM (<= 48 registers) */
 #define NVR_TUNE_NO_CULL_EARLY_OUT 4u  /* cull: always take the 8-tap lookup (disable the coarse-minimum early-out) */
+#define NVR_TUNE_NO_FAR_COLLAPSE 8u    /* evaluate every flagged pair on its own: by default the pairs of a part whose Gaussian
+                                          weights sum to < 1e-20 (part farther than ~0.73 m: blended transforms ~1e-12, canonical
+                                          point = origin to 5e-13 m) share ONE evaluation per part and frame */
 
 /* Device-side work counters of the most recent pass (diagnostics / benchmark accounting). */
 typedef struct NvrCounters {
     int64_t n_points;              /* samples submitted */
     int64_t n_survivors;           /* samples with pnorm < smpl_thresh */
-    int64_t n_pairs[NVR_NUM_PARTS];/* flagged (sample, part) pairs */
+    int64_t n_pairs[NVR_NUM_PARTS];/* (sample, part) pairs EVALUATED (incl. the one shared far-field pair per part) */
+    int64_t n_far_pairs[NVR_NUM_PARTS]; /* flagged pairs answered by the shared far-field pair (NVR_TUNE_NO_FAR_COLLAPSE: 0);
+                                      flagged pairs of the reference = n_pairs + n_far_pairs - (n_far_pairs or collapse on ? 1 : 0) */
     int64_t kernel_launches;       /* kernels this handle has launched since creation */
 } NvrCounters;
 
@@ -336,7 +341,8 @@ typedef struct NvrStageProfile {
     int64_t launches[NVR_NUM_STAGES];
     int64_t passes;
     int64_t survivors;                    /* summed over the profiled passes */
-    int64_t pairs[NVR_NUM_PARTS];
+    int64_t pairs[NVR_NUM_PARTS];         /* evaluated pairs (what the gather and the MLPs processed) */
+    int64_t far_pairs[NVR_NUM_PARTS];     /* pairs answered by the shared far-field pair */
 } NvrStageProfile;
 int nvr_profile(NvrHandle h, int32_t enable);
 int nvr_profile_read(NvrHandle h, NvrStageProfile* out);

@@ -64,12 +64,12 @@ class NvrConfig(C.Structure):
 
 class NvrCounters(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_survivors", C.c_int64), ("n_pairs", C.c_int64 * NUM_PARTS),
-                ("kernel_launches", C.c_int64)]
+                ("n_far_pairs", C.c_int64 * NUM_PARTS), ("kernel_launches", C.c_int64)]
 
 
 class NvrStageProfile(C.Structure):
     _fields_ = [("ms", C.c_double * 7), ("launches", C.c_int64 * 7), ("passes", C.c_int64), ("survivors", C.c_int64),
-                ("pairs", C.c_int64 * NUM_PARTS)]
+                ("pairs", C.c_int64 * NUM_PARTS), ("far_pairs", C.c_int64 * NUM_PARTS)]
 
 
 class NvrAdamTensor(C.Structure):

@@ -268,18 +268,20 @@ static const size_t WS_PER_POINT = sizeof(int) + sizeof(float4) + NVR_NUM_PARTS 
 extern "C" size_t nvr_workspace_bytes(NvrHandle, int64_t max_points) {
     if (max_points < 1) max_points = 1;
     const size_t pts = ((size_t)max_points + 63) & ~(size_t)63;
-    return WS_HEADER + (pts + 64) * WS_PER_POINT;
+    return WS_HEADER + (pts + 128) * WS_PER_POINT;
 }
 
 struct Workspace {
     int* counters; int* surv_of_sample; float4* surv; PairRec* pairs; float* emb; float4* raws;
-    long long cap;
+    long long cap;                          // stride of every per-sample / per-pair array
+    long long pts;                          // samples one pass may hold: cap - 64 (the last survivor slot and one
+                                            // pair record per part belong to the shared far-field pairs, NVR_FAR_WSUM)
 };
 static bool carve(void* ws, size_t bytes, Workspace& w) {
-    if (!ws || bytes < WS_HEADER + 65 * WS_PER_POINT || ((uintptr_t)ws & 255)) return false;
+    if (!ws || bytes < WS_HEADER + 192 * WS_PER_POINT || ((uintptr_t)ws & 255)) return false;
     long long cap = (long long)((bytes - WS_HEADER) / WS_PER_POINT) - 64;
     cap = std::min<long long>(cap & ~63ll, 1ll << 30);
-    if (cap < 64) return false;
+    if (cap < 128) return false;
     char* p = (char*)ws;
     w.counters = (int*)p; p += WS_HEADER;
     w.surv = (float4*)p; p += cap * sizeof(float4);
@@ -288,6 +290,7 @@ static bool carve(void* ws, size_t bytes, Workspace& w) {
     w.emb = (float*)p; p += cap * NVR_NUM_PARTS * NVR_EMB_STRIDE * sizeof(float);
     w.surv_of_sample = (int*)p;
     w.cap = cap;
+    w.pts = cap - 64;
     return true;
 }
 
@@ -312,7 +315,15 @@ static void launch_mlp_tc(NvrEngine* h, int grid, const float* blk, int n_rgb, i
         k_mlp_tc<1><<<grid, TC_THREADS(1), TC_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
 }
 
-// One pass over `n` samples (n <= ws.cap): cull -> warp -> 5x(embed, mlp).  The caller resolves.
+// One pass over `n` samples (n <= ws.pts): cull -> warp -> 5x(embed, mlp).  The caller resolves.
+// Far-field pairs share one evaluation per part (NVR_FAR_WSUM) unless the caller needs every pair's own record
+// (per-stage debug output, training) or NVR_TUNE_NO_FAR_COLLAPSE is set.
+static bool far_collapse(const NvrEngine* h, const float* dbg, const float* out_x0) {
+    return !(h->cfg.tune & NVR_TUNE_NO_FAR_COLLAPSE) && !dbg && !out_x0;
+}
+static const float4* far_raws(const NvrEngine* h, const Workspace& w, bool on) {
+    return on ? w.raws + (w.cap - 1) * NVR_NUM_PARTS : nullptr;
+}
 static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const float* ray_d, const float* near_,
                     const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
                     float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr, bool full_tables = false) {
@@ -323,11 +334,12 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
                                                       w.counters, w.surv_of_sample, w.surv); }
     // neighbour records alias the embedding buffer: they are consumed by k_warp before k_embed writes it
     KnnRec* recs = (KnnRec*)w.emb;
+    const int far_slot = far_collapse(h, dbg, out_x0) ? (int)w.cap - 1 : -1;
     { StageTimer t(h, st, NVR_STAGE_KNN);
     if (h->cfg.tune & NVR_TUNE_KNN_OCC5)        // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
-        k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg);
+        k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot);
     else
-        k_knn<1><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg); }
+        k_knn<4><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot); }
     { StageTimer t(h, st, NVR_STAGE_WARP);
     const dim3 wg(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS);
     if (h->cfg.tune & NVR_TUNE_WARP_OCC8)       // <= 64 registers: 8 CTAs (32 warps) per SM instead of 6
@@ -394,11 +406,11 @@ extern "C" int nvr_query_points(NvrHandle h, const float* wpts, const float* vie
     Workspace w;
     if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_query_points: workspace too small or not 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream_;
-    for (long long s = 0; s < n; s += w.cap) {
-        const long long m = std::min<long long>(w.cap, n - s);
+    for (long long s = 0; s < n; s += w.pts) {
+        const long long m = std::min<long long>(w.pts, n - s);
         if (int rc = run_pass(h, w, wpts + s * 3, nullptr, nullptr, nullptr, m, 0, viewdir + s * 3, 1, st)) return rc;
         { StageTimer t(h, st, NVR_STAGE_RESOLVE);
-        k_resolve_points<<<grid_for(m, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, m, (float4*)raw + s,
+        k_resolve_points<<<grid_for(m, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, far_raws(h, w, far_collapse(h, nullptr, nullptr)), m, (float4*)raw + s,
                                                                            occ ? occ + s : nullptr); }
         NVR_CHECK(h, cudaGetLastError());
         h->launches++;
@@ -415,7 +427,7 @@ extern "C" int nvr_render_rays(NvrHandle h, const float* ray_o, const float* ray
     if (n_rays > 0 && (!ray_o || !ray_d || !near_ || !far_ || !rgb_map || !acc_map)) return fail(h, "nvr_render_rays: null argument");
     Workspace w;
     if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_render_rays: workspace too small or not 256-byte aligned");
-    const long long rays_per_pass = w.cap / n_samples;
+    const long long rays_per_pass = w.pts / n_samples;
     if (rays_per_pass < 1) return fail(h, "nvr_render_rays: workspace smaller than one ray");
     cudaStream_t st = (cudaStream_t)stream_;
     for (long long r = 0; r < n_rays; r += rays_per_pass) {
@@ -424,7 +436,7 @@ extern "C" int nvr_render_rays(NvrHandle h, const float* ray_o, const float* ray
         if (int rc = run_pass(h, w, ray_o + r * 3, ray_d + r * 3, near_ + r, far_ + r, m, n_samples, ray_d + r * 3, n_samples, st))
             return rc;
         { StageTimer t(h, st, NVR_STAGE_RESOLVE);
-        k_resolve_rays<<<grid_for(nr, 8, h->sm_count * 8), 256, 0, st>>>(w.surv_of_sample, w.raws, nr, n_samples, rgb_map + r * 3,
+        k_resolve_rays<<<grid_for(nr, 8, h->sm_count * 8), 256, 0, st>>>(w.surv_of_sample, w.raws, far_raws(h, w, far_collapse(h, nullptr, nullptr)), nr, n_samples, rgb_map + r * 3,
                                                                        acc_map + r, raw ? (float4*)raw + r * n_samples : nullptr); }
         NVR_CHECK(h, cudaGetLastError());
         h->launches++;
@@ -485,7 +497,7 @@ extern "C" int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const f
     if (n > 0 && (!emb || !dirs || !raw)) return fail(h, "nvr_part_mlp: null argument");
     if (n == 0) return 0;
     Workspace w;
-    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_part_mlp: workspace too small");
+    if (!carve(workspace, ws_bytes, w) || w.pts < n) return fail(h, "nvr_part_mlp: workspace too small");
     cudaStream_t st = (cudaStream_t)stream_;
     k_make_pairs<<<(int)((n + 255) / 256), 256, 0, st>>>(dirs, (int)n, w.pairs, w.counters);
     if (h->cfg.mlp_mode >= 1) {
@@ -507,12 +519,12 @@ extern "C" int nvr_query_points_debug(NvrHandle h, const float* wpts, const floa
                                       int32_t* surv_of_sample, float* warp_dbg, void* workspace, size_t ws_bytes, void* stream_) {
     if (int rc = ready(h, "nvr_query_points_debug")) return rc;
     Workspace w;
-    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_query_points_debug: workspace must hold all points in one pass");
+    if (!carve(workspace, ws_bytes, w) || w.pts < n) return fail(h, "nvr_query_points_debug: workspace must hold all points in one pass");
     if (!wpts || !viewdir || !raw || !surv_of_sample || !warp_dbg) return fail(h, "nvr_query_points_debug: null argument");
     cudaStream_t st = (cudaStream_t)stream_;
     NVR_CHECK(h, cudaMemsetAsync(warp_dbg, 0, (size_t)n * NVR_NUM_PARTS * 8 * sizeof(float), st));
     if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, warp_dbg)) return rc;
-    k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, n, (float4*)raw, nullptr);
+    k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, nullptr, n, (float4*)raw, nullptr);
     NVR_CHECK(h, cudaMemcpyAsync(surv_of_sample, w.surv_of_sample, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
@@ -568,14 +580,14 @@ extern "C" int nvr_train_forward(NvrHandle h, const float* wpts, const float* vi
     if (n < 0 || (n > 0 && (!wpts || !viewdir || !raw || !x0 || !resd || !tocc || !sample_of_slot)))
         return fail(h, "nvr_train_forward: null argument");
     Workspace w;
-    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_train_forward: workspace must hold all points in one pass");
+    if (!carve(workspace, ws_bytes, w) || w.pts < n) return fail(h, "nvr_train_forward: workspace must hold all points in one pass");
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
     NVR_CHECK(h, cudaMemsetAsync(x0, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
     NVR_CHECK(h, cudaMemsetAsync(resd, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
     NVR_CHECK(h, cudaMemsetAsync(tocc, 0, (size_t)n * NVR_NUM_PARTS * sizeof(float), st));
     if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, nullptr, x0, resd, true)) return rc;
-    k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, n, (float4*)raw, occ);
+    k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, nullptr, n, (float4*)raw, occ);
     k_export_slots<<<grid_for(n, 256, h->sm_count * 8), 256, 0, st>>>(w.counters, w.surv, w.raws, tocc, sample_of_slot);
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 2;
@@ -606,7 +618,7 @@ extern "C" int nvr_train_backward(NvrHandle h, const float* d_raw, const float* 
     if (int rc = ready(h, "nvr_train_backward")) return rc;
     if (n < 0 || !grads || (n > 0 && (!d_raw || !x0))) return fail(h, "nvr_train_backward: null argument");
     Workspace w;
-    if (!carve(workspace, ws_bytes, w) || w.cap < n) return fail(h, "nvr_train_backward: not the forward's workspace");
+    if (!carve(workspace, ws_bytes, w) || w.pts < n) return fail(h, "nvr_train_backward: not the forward's workspace");
     if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < train_scratch_bytes(w.cap))
         return fail(h, "nvr_train_backward: scratch too small (nvr_train_scratch_bytes) or not 256-byte aligned");
     if (n == 0) return 0;
@@ -877,7 +889,7 @@ extern "C" int nvr_profile_read(NvrHandle h, NvrStageProfile* out) {
     for (int i = 0; i < h->n_pass_snap; ++i) {
         const int* c = h->h_pass_counters + (size_t)i * NVR_CTR_WORDS;
         out->survivors += c[NVR_CTR_SURV];
-        for (int p = 0; p < NVR_NUM_PARTS; ++p) out->pairs[p] += c[NVR_CTR_PAIR + p];
+        for (int p = 0; p < NVR_NUM_PARTS; ++p) { out->pairs[p] += c[NVR_CTR_PAIR + p]; out->far_pairs[p] += c[NVR_CTR_FAR + p]; }
     }
     return 0;
 }
@@ -890,7 +902,7 @@ extern "C" int nvr_read_counters(NvrHandle h, NvrCounters* out, void* stream_) {
     NVR_CHECK(h, cudaStreamSynchronize((cudaStream_t)stream_));
     out->n_points = h->last_points;
     out->n_survivors = host[NVR_CTR_SURV];
-    for (int p = 0; p < NVR_NUM_PARTS; ++p) out->n_pairs[p] = host[NVR_CTR_PAIR + p];
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) { out->n_pairs[p] = host[NVR_CTR_PAIR + p]; out->n_far_pairs[p] = host[NVR_CTR_FAR + p]; }
     out->kernel_launches = h->launches;
     return 0;
 }

@@ -21,7 +21,19 @@
 #define NVR_EMB_STRIDE 20          // 19 used
 #define NVR_CTR_SURV 0
 #define NVR_CTR_PAIR 1             // [1..5]
+#define NVR_CTR_FAR 6              // [6..10] flagged pairs answered by the part's shared far-field pair
 #define NVR_CTR_WORDS 16
+// Far-field pairs.  A part farther than ~0.73 m from a sample still gets flagged (its Gaussian weights sum to far less
+// than the 1e-8 in the normalisation, so pdist -> 0 < smpl_thresh: DESIGN.md section 1).  Once sum(w) < NVR_FAR_WSUM the
+// normalised weights are < 1e-12, the blended transforms are ~1e-12, and the canonical point and direction the part
+// network sees are the origin to within 5e-13 m / 1e-29 -- far below one fp32 ulp of everything they are added to
+// (the residual, the bbox corner).  All such pairs of a part therefore share ONE evaluation: k_knn answers them with a
+// marker (occ = -1) and appends a single zero-weight pair per part whose result every marker resolves to.
+#define NVR_FAR_WSUM 1e-20f
+// 4 exp(-d2 / 0.01125) < 1e-20  <=>  d2 > 0.01125 (ln 4 + 20 ln 10) = 0.5337: when even the nearest cluster box of a part is
+// farther than this from the box of a warp's queries, all its lanes are far-field for the part and the 4-NN search is
+// skipped (1 % margin on the exponent for expf / lower-bound rounding).
+#define NVR_FAR_D2 0.54f
 
 struct __align__(16) PairRec {     // one flagged (sample, part) pair: 32 B
     float x, y, z;                 // canonical (big pose + residual) point
@@ -248,15 +260,17 @@ __device__ __forceinline__ float box_reach2(const float4& lo, const float4& hi, 
     return dx * dx + dy * dy + dz * dz;
 }
 
-__device__ __forceinline__ void knn_part_group(const FrameDev& fr, int part, const float p[3], bool live,
-                                               const float qlo[3], const float qhi[3], Knn4& k) {
+// Returns true (and leaves k untouched) when allow_far and the whole part is far-field for every query of the warp.
+__device__ __forceinline__ bool knn_part_group(const FrameDev& fr, int part, const float p[3], bool live,
+                                               const float qlo[3], const float qhi[3], Knn4& k, bool allow_far) {
     const int lane = threadIdx.x & 31;
     const int c0 = fr.cl_off[part], ncl = fr.cl_off[part + 1] - c0;
-    if (ncl <= 0) return;
+    if (ncl <= 0) return false;
     float U = INFINITY, best = INFINITY;
-    int seed = 0;
+    int seed = 0, nv = 0;
     for (int c = lane; c < ncl; c += 32) {
         const float4 lo = __ldg(fr.cl_lo + c0 + c), hi = __ldg(fr.cl_hi + c0 + c);
+        nv += __float_as_int(lo.w);
         if (__float_as_int(lo.w) >= NVR_KNN) U = fminf(U, box_reach2(lo, hi, qlo, qhi));
         const float g = box_gap2(lo, hi, qlo, qhi);
         if (g < best) { best = g; seed = c; }
@@ -268,6 +282,9 @@ __device__ __forceinline__ void knn_part_group(const FrameDev& fr, int part, con
         const int os = __shfl_xor_sync(0xffffffffu, seed, d);
         if (ob < best || (ob == best && os < seed)) { best = ob; seed = os; }
     }
+    // every vertex of the part is farther than sqrt(best) from every query: with >= 4 real vertices all four
+    // neighbours are, so sum(w) < NVR_FAR_WSUM for every lane whatever the search would return
+    if (allow_far && best > NVR_FAR_D2 && __reduce_add_sync(0xffffffffu, nv) >= NVR_KNN) return true;
     U *= 1.00001f;
     // round -1 holds only the seed (every live lane scans it: its 4th-best is still +inf); rounds 0.. hold the rest
     for (int cb = -32; cb < ncl; cb += 32) {
@@ -291,6 +308,7 @@ __device__ __forceinline__ void knn_part_group(const FrameDev& fr, int part, con
             if (__any_sync(0xffffffffu, need)) nvr_knn_scan(fr.verts + (long long)(c0 + cc) * NVR_CL, p, k);
         }
     }
+    return false;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -363,11 +381,21 @@ struct __align__(16) KnnRec {      // a flagged (sample, part) pair before the w
 
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB)
-k_knn(FrameDev fr, float thresh, int* __restrict__ counters, const float4* __restrict__ surv,
-      KnnRec* __restrict__ recs, int cap, float4* __restrict__ raws, float* __restrict__ dbg) {
+k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict__ surv,
+      KnnRec* __restrict__ recs, int cap, float4* __restrict__ raws, float* __restrict__ dbg, int far_slot) {
     // dbg (optional, per SAMPLE): [n][5][8] = flag, x, y, z, vx, vy, vz, pdist -- per-stage parity tests
+    // far_slot >= 0: survivor slot reserved for the shared far-field pairs (NVR_FAR_WSUM); -1 = evaluate every pair
     const int n_surv = counters[NVR_CTR_SURV];
     const int lane = threadIdx.x & 31;
+    if (far_slot >= 0 && blockIdx.x == 0 && threadIdx.x < NVR_PARTS && n_surv > 0) {
+        const int part = threadIdx.x;
+        if (part == 0) surv[far_slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        KnnRec rec;                                               // zero weights: blended transforms, point and direction are 0
+#pragma unroll
+        for (int i = 0; i < NVR_KNN; ++i) { rec.w[i] = 0.0f; rec.idx[i] = 0; }
+        rec.surv = far_slot; rec._pad[0] = rec._pad[1] = rec._pad[2] = 0;
+        recs[(long long)part * cap + atomicAdd(&counters[NVR_CTR_PAIR + part], 1)] = rec;
+    }
     // warp-uniform trip count so the ballots below see full warps
     for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_surv; base += gridDim.x * blockDim.x) {
         const int s = base + lane;
@@ -394,18 +422,28 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, const float4* __res
         for (int part = 0; part < NVR_PARTS; ++part) {
             Knn4 k;
             nvr_knn_init(k);
-            knn_part_group(fr, part, p, live, qlo, qhi, k);
+            const bool all_far = knn_part_group(fr, part, p, live, qlo, qhi, k, far_slot >= 0);
             bool flag = false;
             KnnRec rec;
-            if (live) {
-                const float pdist = nvr_knn_weights(k, rec.w);
+            bool far = live && all_far;
+            if (far) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, -1.0f);
+            if (live && !all_far) {
+                float wsum;
+                const float pdist = nvr_knn_weights(k, rec.w, &wsum);
                 flag = pdist < thresh;                             // inb_part_network_multiassign.py:90
+                far = flag && far_slot >= 0 && wsum < NVR_FAR_WSUM;
+                if (far) {                                         // answered by the part's shared far-field pair
+                    raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, -1.0f);
+                    flag = false;
+                }
                 if (dbg) {
                     float* dr = dbg + ((long long)sample * NVR_PARTS + part) * 8;
                     dr[0] = flag ? 1.0f : 0.0f; dr[7] = pdist;
                 }
-                if (!flag) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, 0.f);   // :201-202
+                if (!flag && !far) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, 0.f);   // :201-202
             }
+            const unsigned fballot = __ballot_sync(0xffffffffu, far);
+            if (fballot && lane == 0) atomicAdd(&counters[NVR_CTR_FAR + part], __popc(fballot));
             const unsigned ballot = __ballot_sync(0xffffffffu, flag);
             if (ballot) {
                 int wbase = 0;
@@ -823,22 +861,25 @@ __global__ void k_make_pairs(const float* __restrict__ dirs, int n, PairRec* __r
 // -----------------------------------------------------------------------------------------
 // resolve: arg-max over parts, scatter to samples, composite along rays
 // -----------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 fuse_parts(const float4* __restrict__ raws, int slot) {
-    // inb_part_network_multiassign.py:253-255: raw of the part with the largest occupancy (first on ties)
+__device__ __forceinline__ float4 fuse_parts(const float4* __restrict__ raws, int slot, const float4* __restrict__ far_raws) {
+    // inb_part_network_multiassign.py:253-255: raw of the part with the largest occupancy (first on ties).
+    // occ = -1 marks a pair answered by the part's shared far-field evaluation far_raws[p] (NVR_FAR_WSUM).
     float4 best = raws[(long long)slot * NVR_PARTS];
+    if (best.w < 0.0f) best = far_raws[0];
 #pragma unroll
     for (int p = 1; p < NVR_PARTS; ++p) {
-        const float4 r = raws[(long long)slot * NVR_PARTS + p];
+        float4 r = raws[(long long)slot * NVR_PARTS + p];
+        if (r.w < 0.0f) r = far_raws[p];
         if (r.w > best.w) best = r;
     }
     return best;
 }
 
-__global__ void k_resolve_points(const int* __restrict__ surv_of_sample, const float4* __restrict__ raws, long long n,
-                                 float4* __restrict__ raw_out, float* __restrict__ occ_out) {
+__global__ void k_resolve_points(const int* __restrict__ surv_of_sample, const float4* __restrict__ raws, const float4* __restrict__ far_raws,
+                                 long long n, float4* __restrict__ raw_out, float* __restrict__ occ_out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int slot = surv_of_sample[i];
-        const float4 r = slot >= 0 ? fuse_parts(raws, slot) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 r = slot >= 0 ? fuse_parts(raws, slot, far_raws) : make_float4(0.f, 0.f, 0.f, 0.f);
         raw_out[i] = r;
         if (occ_out) occ_out[i] = r.w;
     }
@@ -847,8 +888,8 @@ __global__ void k_resolve_points(const int* __restrict__ surv_of_sample, const f
 // One warp per ray; samples are walked 32 at a time with a shuffle product-scan of (1 - alpha)
 // (net_utils.py:12-15 with epsilon = 0; :39-41).
 __global__ void __launch_bounds__(256)
-k_resolve_rays(const int* __restrict__ surv_of_sample, const float4* __restrict__ raws, long long n_rays, int S,
-               float* __restrict__ rgb_map, float* __restrict__ acc_map, float4* __restrict__ raw_out) {
+k_resolve_rays(const int* __restrict__ surv_of_sample, const float4* __restrict__ raws, const float4* __restrict__ far_raws,
+               long long n_rays, int S, float* __restrict__ rgb_map, float* __restrict__ acc_map, float4* __restrict__ raw_out) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -859,7 +900,7 @@ k_resolve_rays(const int* __restrict__ surv_of_sample, const float4* __restrict_
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < S) {
                 const int slot = surv_of_sample[ray * S + k];
-                if (slot >= 0) r = fuse_parts(raws, slot);
+                if (slot >= 0) r = fuse_parts(raws, slot, far_raws);
                 if (raw_out) raw_out[ray * S + k] = r;
             }
             float incl = 1.0f - r.w;                              // inclusive product of (1 - alpha)

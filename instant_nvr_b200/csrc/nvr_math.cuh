@@ -413,7 +413,7 @@ NVR_HD float nvr_aabb_lb(const float4& lo, const float4& hi, const float p[3]) {
 
 // From the 4 neighbours to their normalised Gaussian weights and the weighted distance:
 // sample_blend_closest_points, :741-748.
-NVR_HD float nvr_knn_weights(const Knn4& k, float w[NVR_KNN]) {
+NVR_HD float nvr_knn_weights(const Knn4& k, float w[NVR_KNN], float* wsum_out = nullptr) {
     float d[NVR_KNN], wsum = 0.0f;
 #pragma unroll
     for (int i = 0; i < NVR_KNN; ++i) {
@@ -421,6 +421,7 @@ NVR_HD float nvr_knn_weights(const Knn4& k, float w[NVR_KNN]) {
         w[i] = expf(-(d[i] * d[i]) / 0.01125f);                  // :746, 2*radius^2 = 2*0.075^2
         wsum += w[i];
     }
+    if (wsum_out) *wsum_out = wsum;
     const float denom = wsum + 1e-8f;                            // :747
     float pdist = 0.0f;
 #pragma unroll

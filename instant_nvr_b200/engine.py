@@ -72,7 +72,7 @@ def _params_struct(net, grads: Optional[Dict[str, torch.Tensor]] = None) -> "cab
 
 class Engine:
     def __init__(self, cfg: PathConfig, device: Optional[torch.device] = None, max_points_per_pass: int = 32 << 20,
-                 mlp_mode: Optional[int] = None, inference_tables: Optional[bool] = None):
+                 mlp_mode: Optional[int] = None, inference_tables: Optional[bool] = None, tune: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("instant_nvr_b200 needs a CUDA device: the hot path has no CPU implementation")
         cfg.check_supported()
@@ -86,7 +86,7 @@ class Engine:
         self.lib = cabi.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.max_points_per_pass = int(os.environ.get("NVR_PASS_POINTS", max_points_per_pass))
-        self.tune = int(os.environ.get("NVR_TUNE", DEFAULT_TUNE))      # NVR_TUNE_* bits of include/nvr_b200.h
+        self.tune = int(os.environ.get("NVR_TUNE", DEFAULT_TUNE)) if tune is None else int(tune)   # NVR_TUNE_* bits of include/nvr_b200.h
         conf = cabi.NvrConfig(cabi.ABI_VERSION, self.device.index or 0, float(cfg.smpl_thresh), int(mlp_mode), self.tune, 0)
         h = C.c_void_p()
         rc = self.lib.nvr_create(C.byref(conf), C.byref(h))
@@ -360,10 +360,10 @@ class Engine:
         p = cabi.NvrStageProfile()
         self._check(self.lib.nvr_profile_read(self._h, C.byref(p)), "nvr_profile_read")
         return {"ms": dict(zip(cabi.STAGE_NAMES, list(p.ms))), "launches": dict(zip(cabi.STAGE_NAMES, list(p.launches))),
-                "passes": p.passes, "survivors": p.survivors, "pairs": list(p.pairs)}
+                "passes": p.passes, "survivors": p.survivors, "pairs": list(p.pairs), "far_pairs": list(p.far_pairs)}
 
     def counters(self) -> Dict[str, int]:
         c = cabi.NvrCounters()
         self._check(self.lib.nvr_read_counters(self._h, C.byref(c), _stream_ptr()), "nvr_read_counters")
         return {"n_points": c.n_points, "n_survivors": c.n_survivors, "n_pairs": list(c.n_pairs),
-                "kernel_launches": c.kernel_launches}
+                "n_far_pairs": list(c.n_far_pairs), "kernel_launches": c.kernel_launches}

@@ -283,6 +283,36 @@ def test_render_host_and_multipass_match(gpu):
     diag("counters_last_pass", **{k: v for k, v in c.items()})
 
 
+@pytest.mark.parametrize("gain", [1.0, 200.0])
+def test_far_field_pairs_share_one_evaluation(gpu, gain):
+    """Default mode answers every flagged pair whose Gaussian weights sum to < 1e-20 (part farther than ~0.73 m) with ONE
+    shared zero-weight evaluation per part (csrc/nvr_kernels.cuh NVR_FAR_WSUM); NVR_TUNE_NO_FAR_COLLAPSE evaluates each
+    pair on its own, as the reference does.  The canonical points differ by < 5e-13 m, which fp32 absorbs: the two
+    modes must agree to 1e-6 on every sample and bit for bit on (nearly) all of them; the pair accounting must add up."""
+    from instant_nvr_b200.engine import Engine
+    cfg, gb, net = gpu["cfg"], gpu["gbatch"], gpu["nets"][gain]
+    S = cfg.N_samples
+    out = {}
+    for tune in (0, 8):
+        eng = Engine(cfg, tune=tune)
+        eng.bind_params(net)
+        rgb, acc, raw = eng.render_rays(gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0], S, want_raw=True, batch=gb)
+        out[tune] = (rgb, acc, raw, eng.counters())
+    (rgb0, acc0, raw0, c0), (rgb8, acc8, raw8, c8) = out[0], out[8]
+    assert sum(c8["n_far_pairs"]) == 0 and sum(c0["n_far_pairs"]) > 0
+    assert c0["n_survivors"] == c8["n_survivors"] > 0
+    for p in range(5):
+        assert c8["n_pairs"][p] == c0["n_pairs"][p] - 1 + c0["n_far_pairs"][p], p
+    d = (raw0 - raw8).abs()
+    differ = int((d.max(dim=-1).values > 0).sum())
+    active = int((raw8[..., 3] > 0).sum())
+    diag("far_collapse", gain=gain, far_pairs=c0["n_far_pairs"], evaluated=c0["n_pairs"], flagged=c8["n_pairs"],
+         max_abs=d.max().item(), samples_not_bitwise_equal=differ, active=active,
+         rgb_max_abs=(rgb0 - rgb8).abs().max().item())
+    assert d.max().item() <= 1e-6 and differ <= max(2, active // 1000)
+    assert (rgb0 - rgb8).abs().max().item() <= 1e-6 and (acc0 - acc8).abs().max().item() <= 1e-6
+
+
 def test_edge_cases(gpu):
     cfg, net, gb = gpu["cfg"], gpu["nets"][1.0], gpu["gbatch"]
     eng = net.engine()
