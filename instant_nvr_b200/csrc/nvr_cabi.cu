@@ -598,7 +598,8 @@ extern "C" int nvr_train_forward(NvrHandle h, const float* wpts, const float* vi
 static size_t train_scratch_bytes(long long cap) {
     return 256 + (size_t)cap * NVR_NUM_PARTS * (sizeof(GradRec) + (NVR_EMB_STRIDE + 9) * sizeof(float));
 }
-extern "C" size_t nvr_train_scratch_bytes(NvrHandle, int64_t n) { return train_scratch_bytes(((n < 1 ? 1 : n) + 63) & ~63ll); }
+// sized for the stride of a workspace of nvr_workspace_bytes(n): carve() gives cap = round_up(n, 64) + 64
+extern "C" size_t nvr_train_scratch_bytes(NvrHandle, int64_t n) { return train_scratch_bytes((((n < 1 ? 1 : n) + 63) & ~63ll) + 64); }
 
 static PartMlpGrad mlp_grad(const NvrPart& g, int n_rgb) {
     PartMlpGrad o;

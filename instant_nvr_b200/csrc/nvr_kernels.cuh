@@ -34,6 +34,13 @@
 // farther than this from the box of a warp's queries, all its lanes are far-field for the part and the 4-NN search is
 // skipped (1 % margin on the exponent for expf / lower-bound rounding).
 #define NVR_FAR_D2 0.54f
+// Certainly-unflagged parts.  pdist = sum(w d) / (sum(w) + 1e-8) >= dmin * sum(w) / (sum(w) + 1e-8).  When every vertex of
+// the part is at least dmin = 1.04 smpl_thresh from every query of the warp (5.2 cm) and the 4th-nearest distance of
+// every query is at most sqrt(NVR_REACH_D2) = 0.41 m (then sum(w) >= 4 exp(-0.17 / 0.01125) = 1.1e-6 and the ratio is
+// >= 0.991), pdist >= 1.03 smpl_thresh: the part is NOT flagged for any lane, whatever its exact neighbours are, and
+// the search is skipped.
+#define NVR_GAP_FACTOR2 1.0816f    // 1.04^2
+#define NVR_REACH_D2 0.17f
 
 struct __align__(16) PairRec {     // one flagged (sample, part) pair: 32 B
     float x, y, z;                 // canonical (big pose + residual) point
@@ -260,12 +267,16 @@ __device__ __forceinline__ float box_reach2(const float4& lo, const float4& hi, 
     return dx * dx + dy * dy + dz * dz;
 }
 
-// Returns true (and leaves k untouched) when allow_far and the whole part is far-field for every query of the warp.
-__device__ __forceinline__ bool knn_part_group(const FrameDev& fr, int part, const float p[3], bool live,
-                                               const float qlo[3], const float qhi[3], Knn4& k, bool allow_far) {
+// Returns KNN_FAR / KNN_UNFLAGGED (and leaves k untouched) when allow_skip and the whole part is far-field / certainly
+// unflagged for every query of the warp; KNN_SEARCHED otherwise.
+#define KNN_SEARCHED 0
+#define KNN_FAR 1
+#define KNN_UNFLAGGED 2
+__device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, const float p[3], bool live,
+                                              const float qlo[3], const float qhi[3], Knn4& k, bool allow_skip, float thresh) {
     const int lane = threadIdx.x & 31;
     const int c0 = fr.cl_off[part], ncl = fr.cl_off[part + 1] - c0;
-    if (ncl <= 0) return false;
+    if (ncl <= 0) return KNN_SEARCHED;
     float U = INFINITY, best = INFINITY;
     int seed = 0, nv = 0;
     for (int c = lane; c < ncl; c += 32) {
@@ -284,7 +295,9 @@ __device__ __forceinline__ bool knn_part_group(const FrameDev& fr, int part, con
     }
     // every vertex of the part is farther than sqrt(best) from every query: with >= 4 real vertices all four
     // neighbours are, so sum(w) < NVR_FAR_WSUM for every lane whatever the search would return
-    if (allow_far && best > NVR_FAR_D2 && __reduce_add_sync(0xffffffffu, nv) >= NVR_KNN) return true;
+    if (allow_skip && best > NVR_FAR_D2 && __reduce_add_sync(0xffffffffu, nv) >= NVR_KNN) return KNN_FAR;
+    // U is finite only if some cluster holds >= 4 real vertices, so the four neighbours are real here too
+    if (allow_skip && best > NVR_GAP_FACTOR2 * thresh * thresh && U <= NVR_REACH_D2) return KNN_UNFLAGGED;
     U *= 1.00001f;
     // round -1 holds only the seed (every live lane scans it: its 4th-best is still +inf); rounds 0.. hold the rest
     for (int cb = -32; cb < ncl; cb += 32) {
@@ -308,7 +321,7 @@ __device__ __forceinline__ bool knn_part_group(const FrameDev& fr, int part, con
             if (__any_sync(0xffffffffu, need)) nvr_knn_scan(fr.verts + (long long)(c0 + cc) * NVR_CL, p, k);
         }
     }
-    return false;
+    return KNN_SEARCHED;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -422,12 +435,13 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
         for (int part = 0; part < NVR_PARTS; ++part) {
             Knn4 k;
             nvr_knn_init(k);
-            const bool all_far = knn_part_group(fr, part, p, live, qlo, qhi, k, far_slot >= 0);
+            const int group = knn_part_group(fr, part, p, live, qlo, qhi, k, far_slot >= 0, thresh);
             bool flag = false;
             KnnRec rec;
-            bool far = live && all_far;
+            bool far = live && group == KNN_FAR;
             if (far) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, -1.0f);
-            if (live && !all_far) {
+            if (live && group == KNN_UNFLAGGED) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, 0.f);   // :201-202
+            if (live && group == KNN_SEARCHED) {
                 float wsum;
                 const float pdist = nvr_knn_weights(k, rec.w, &wsum);
                 flag = pdist < thresh;                             // inb_part_network_multiassign.py:90

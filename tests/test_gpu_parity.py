@@ -407,6 +407,7 @@ def test_full_size_properties_c2(full):
     #     per-ray results do not depend on neighbours or on compaction order)
     perm = torch.randperm(512 * 512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))[:20000]
     rgb_p, acc_p, raw_p = eng.render_rays(o[perm], d[perm], n[perm], f[perm], S, want_raw=True)
+    c_perm = eng.counters()
     assert torch.equal(rgb_p, rgb[perm]) and torch.equal(acc_p, acc[perm])
     # (2) the two entry points agree: querying the same sample points gives the same raw
     pts = (o[perm][:512, None] + d[perm][:512, None] * (n[perm][:512, None, None] * (1 - torch.linspace(0, 1, S, device="cuda"))[None, :, None]
@@ -420,6 +421,23 @@ def test_full_size_properties_c2(full):
     alpha = raw_p.view(-1, S, 4)[..., 3].double()
     acc_ref = 1 - torch.prod(1 - alpha, dim=-1)
     assert (acc_p.double() - acc_ref).abs().max() < 1e-5
+    # (4) the KNN short cuts (far-field pairs share one evaluation, certainly-unflagged parts skip the search) against
+    #     the every-pair evaluation (NVR_TUNE_NO_FAR_COLLAPSE) on the same 2.56 M samples, full-size tables
+    from instant_nvr_b200.engine import Engine
+    c0 = c_perm
+    eng8 = Engine(cfg, tune=8)
+    eng8.bind_params(net)
+    rgb_8, acc_8, raw_8 = eng8.render_rays(o[perm], d[perm], n[perm], f[perm], S, want_raw=True, batch=gb)
+    c8 = eng8.counters()
+    dr = (raw_8 - raw_p).abs()
+    differ = int((dr.max(dim=-1).values > 0).sum())
+    diag("c2_far_collapse", far_pairs=c0["n_far_pairs"], evaluated=c0["n_pairs"], flagged=c8["n_pairs"], max_abs=dr.max().item(),
+         samples_not_bitwise_equal=differ, survivors=c8["n_survivors"])
+    assert c0["n_survivors"] == c8["n_survivors"]
+    for p in range(5):
+        assert c8["n_pairs"][p] == c0["n_pairs"][p] - 1 + c0["n_far_pairs"][p], p
+    assert dr.max().item() <= 1e-6 and differ <= max(2, c8["n_survivors"] // 10000)
+    assert (rgb_8 - rgb_p).abs().max().item() <= 1e-6
 
 
 def test_full_size_properties_c4_c5(full):
