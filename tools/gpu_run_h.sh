@@ -7,6 +7,6 @@ grep -E "passed|failed|error|rc=|FAILED|Error" gpurun_out/pytest_gpu.log | tail 
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -3 gpurun_out/smoke.log
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 NVR_TUNE=8 timeout 300 python bench.py --steps 20 --warmup 3 --steps-only > gpurun_out/bench_tune8.json 2> gpurun_out/bench_tune8.err; echo "tune8 rc=$?"; cat gpurun_out/bench_tune8.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_" -s 64 -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --steps-only > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^k_" -s 64 -c 17 -o gpurun_out/prof_full -f python bench.py --steps 1 --warmup 3 --steps-only > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_" -s 58 -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --steps-only > gpurun_out/ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^k_" -s 58 -c 17 -o gpurun_out/prof_full -f python bench.py --steps 1 --warmup 3 --steps-only > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | head -40
