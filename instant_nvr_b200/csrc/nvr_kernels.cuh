@@ -329,54 +329,93 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
 // -----------------------------------------------------------------------------------------
 // ray mode  (n_samples > 0): sample i = ray i / n_samples, step i % n_samples; pts = ray_o, aux = ray_d
 // point mode (n_samples == 0): pts = wpts (n,3)
+// Ray mode walks the samples DEPTH-MAJOR inside groups of 32 consecutive rays (position j -> ray 32 g + j % 32, step
+// (j / 32) % S), so the survivor list -- and with it every later kernel's warps -- holds neighbouring pixels at one
+// depth (a few cm across) instead of the entry and exit shells of one ray (tens of cm apart): tighter KNN query
+// boxes, shared neighbour rows and grid cells.  A CTA compacts CULL_T chunks of 256 positions (64 depth steps of one
+// ray group) in shared memory and appends them with ONE atomic, so the runs of neighbouring survivors are hundreds
+// long and the survivor records leave as coalesced 16-byte stores.  Results are per sample and do not depend on the
+// order.
+#define CULL_T 8
 __global__ void __launch_bounds__(256)
 k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray_d,
        const float* __restrict__ near_, const float* __restrict__ far_, long long n, int n_samples,
        float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv) {
+    __shared__ float4 s_surv[256 * CULL_T];
+    __shared__ short s_slot[256 * CULL_T];                        // slot inside the CTA's run, -1 = culled, -2 = no sample
     __shared__ int warp_cnt[8];
-    __shared__ int block_base;
+    __shared__ int s_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (long long base = (long long)blockIdx.x * 256; base < n; base += (long long)gridDim.x * 256) {
-        const long long i = base + threadIdx.x;
-        bool keep = false;
-        float p[3] = {0.f, 0.f, 0.f};
-        if (i < n) {
-            float w[3];
+    const long long n_rays = n_samples > 0 ? n / n_samples : 0;
+    const long long group = 32ll * (n_samples > 0 ? n_samples : 1);
+    const long long n_map = n_samples > 0 ? ((n_rays + 31) / 32) * group : n;
+    for (long long sbase = (long long)blockIdx.x * (256 * CULL_T); sbase < n_map; sbase += (long long)gridDim.x * (256 * CULL_T)) {
+        int run = 0;                                              // survivors of the earlier chunks (same in every thread)
+#pragma unroll 1
+        for (int t = 0; t < CULL_T; ++t) {
+            const long long j = sbase + t * 256 + threadIdx.x;
+            long long i = j, r = 0;                               // i = sample id
+            bool valid = j < n;
+            int k = 0;
             if (n_samples > 0) {
-                const long long r = i / n_samples;
-                const int k = (int)(i - r * n_samples);
-                const float o[3] = {pts[r * 3], pts[r * 3 + 1], pts[r * 3 + 2]};
-                const float d[3] = {ray_d[r * 3], ray_d[r * 3 + 1], ray_d[r * 3 + 2]};
-                nvr_ray_sample(o, d, near_[r], far_[r], k, n_samples, w);
-            } else {
-                w[0] = pts[i * 3]; w[1] = pts[i * 3 + 1]; w[2] = pts[i * 3 + 2];
+                const long long g = j / group;
+                const int w = (int)(j - g * group);
+                k = w >> 5;
+                r = g * 32 + (w & 31);
+                valid = j < n_map && r < n_rays;
+                i = r * n_samples + k;
             }
-            nvr_world_to_pose(fr.R, fr.Th, w, p);
-            float c[3];
-            nvr_volume_coords(fr.dist, p, c);
-            if (!(fr.dist_cmin && nvr_cull_early_out(fr.dist, fr.dist_cmin, c, thresh))) {
-                float pn;
-                nvr_sample_volume_at(fr.dist, c, 0, 1, &pn);
-                keep = pn < thresh;                               // inb_part_network_multiassign.py:136
+            bool keep = false;
+            float p[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+                float w[3];
+                if (n_samples > 0) {
+                    const float o[3] = {pts[r * 3], pts[r * 3 + 1], pts[r * 3 + 2]};
+                    const float d[3] = {ray_d[r * 3], ray_d[r * 3 + 1], ray_d[r * 3 + 2]};
+                    nvr_ray_sample(o, d, near_[r], far_[r], k, n_samples, w);
+                } else {
+                    w[0] = pts[i * 3]; w[1] = pts[i * 3 + 1]; w[2] = pts[i * 3 + 2];
+                }
+                nvr_world_to_pose(fr.R, fr.Th, w, p);
+                float c[3];
+                nvr_volume_coords(fr.dist, p, c);
+                if (!(fr.dist_cmin && nvr_cull_early_out(fr.dist, fr.dist_cmin, c, thresh))) {
+                    float pn;
+                    nvr_sample_volume_at(fr.dist, c, 0, 1, &pn);
+                    keep = pn < thresh;                           // inb_part_network_multiassign.py:136
+                }
             }
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_cnt[wid] = __popc(ballot);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) warp_cnt[wid] = __popc(ballot);
+            __syncthreads();
+            int off = run;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; warp_cnt[w] = tot; tot += c; }
-            block_base = tot ? atomicAdd(&counters[NVR_CTR_SURV], tot) : 0;
-        }
-        __syncthreads();
-        if (i < n) {
-            int slot = -1;
+            for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; off += w < wid ? c : 0; run += c; }
+            int ls = valid ? -1 : -2;
             if (keep) {
-                slot = block_base + warp_cnt[wid] + __popc(ballot & ((1u << lane) - 1u));
-                surv[slot] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));   // passes are < 2^31 samples
+                ls = off + __popc(ballot & ((1u << lane) - 1u));
+                s_surv[ls] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));   // passes are < 2^31 samples
             }
-            surv_of_sample[i] = slot;
+            s_slot[t * 256 + threadIdx.x] = (short)ls;
+            __syncthreads();                                      // warp_cnt is rewritten by the next chunk
+        }
+        const int total = run;
+        if (threadIdx.x == 0) s_base = total ? atomicAdd(&counters[NVR_CTR_SURV], total) : 0;
+        __syncthreads();
+        const int gbase = s_base;
+        for (int x = threadIdx.x; x < total; x += 256) surv[gbase + x] = s_surv[x];
+#pragma unroll 1
+        for (int t = 0; t < CULL_T; ++t) {
+            const int ls = s_slot[t * 256 + threadIdx.x];
+            if (ls == -2) continue;
+            const long long j = sbase + t * 256 + threadIdx.x;
+            long long i = j;
+            if (n_samples > 0) {
+                const long long g = j / group;
+                const int w = (int)(j - g * group);
+                i = (g * 32 + (w & 31)) * n_samples + (w >> 5);
+            }
+            surv_of_sample[i] = ls >= 0 ? gbase + ls : -1;
         }
         __syncthreads();
     }
