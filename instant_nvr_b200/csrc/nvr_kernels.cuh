@@ -337,39 +337,50 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
 // long and the survivor records leave as coalesced 16-byte stores.  Results are per sample and do not depend on the
 // order.
 #define CULL_T 8
+#define CULL_SPAN (256 * CULL_T)
+// position inside the walk -> (ray, step, sample id).  g0 / w0: group index and offset of the CTA's first position
+// (one 64-bit division per 2048 positions); everything per position is 32-bit.
+struct CullWalk { long long g0; unsigned w0, group; int S; long long n_rays; };
+__device__ __forceinline__ bool cull_locate(const CullWalk& cw, int local, long long& r, int& k, long long& i) {
+    const unsigned wl = cw.w0 + (unsigned)local;
+    const unsigned q = wl / cw.group, w = wl - q * cw.group;
+    k = (int)(w >> 5);
+    r = (cw.g0 + q) * 32 + (w & 31);
+    i = r * cw.S + k;
+    return r < cw.n_rays;
+}
+
 __global__ void __launch_bounds__(256)
 k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray_d,
        const float* __restrict__ near_, const float* __restrict__ far_, long long n, int n_samples,
        float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv) {
-    __shared__ float4 s_surv[256 * CULL_T];
-    __shared__ short s_slot[256 * CULL_T];                        // slot inside the CTA's run, -1 = culled, -2 = no sample
+    __shared__ float4 s_surv[CULL_SPAN];
+    __shared__ short s_slot[64 * 33];                             // [depth step][ray] (+1 pad): slot in the CTA's run, -1 = culled, -2 = no sample
     __shared__ int warp_cnt[8];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long n_rays = n_samples > 0 ? n / n_samples : 0;
-    const long long group = 32ll * (n_samples > 0 ? n_samples : 1);
-    const long long n_map = n_samples > 0 ? ((n_rays + 31) / 32) * group : n;
-    for (long long sbase = (long long)blockIdx.x * (256 * CULL_T); sbase < n_map; sbase += (long long)gridDim.x * (256 * CULL_T)) {
+    const bool rays = n_samples > 0;
+    CullWalk cw;
+    cw.S = rays ? n_samples : 1;
+    cw.group = 32u * (unsigned)cw.S;
+    cw.n_rays = rays ? n / n_samples : 0;
+    const long long n_map = rays ? ((cw.n_rays + 31) / 32) * (long long)cw.group : n;
+    for (long long sbase = (long long)blockIdx.x * CULL_SPAN; sbase < n_map; sbase += (long long)gridDim.x * CULL_SPAN) {
+        cw.g0 = sbase / (long long)cw.group;
+        cw.w0 = (unsigned)(sbase - cw.g0 * (long long)cw.group);
         int run = 0;                                              // survivors of the earlier chunks (same in every thread)
 #pragma unroll 1
         for (int t = 0; t < CULL_T; ++t) {
-            const long long j = sbase + t * 256 + threadIdx.x;
-            long long i = j, r = 0;                               // i = sample id
-            bool valid = j < n;
+            const int local = t * 256 + threadIdx.x;
+            long long i = sbase + local, r = 0;                   // i = sample id
             int k = 0;
-            if (n_samples > 0) {
-                const long long g = j / group;
-                const int w = (int)(j - g * group);
-                k = w >> 5;
-                r = g * 32 + (w & 31);
-                valid = j < n_map && r < n_rays;
-                i = r * n_samples + k;
-            }
+            bool valid = i < n;
+            if (rays) valid = cull_locate(cw, local, r, k, i) && sbase + local < n_map;
             bool keep = false;
             float p[3] = {0.f, 0.f, 0.f};
             if (valid) {
                 float w[3];
-                if (n_samples > 0) {
+                if (rays) {
                     const float o[3] = {pts[r * 3], pts[r * 3 + 1], pts[r * 3 + 2]};
                     const float d[3] = {ray_d[r * 3], ray_d[r * 3 + 1], ray_d[r * 3 + 2]};
                     nvr_ray_sample(o, d, near_[r], far_[r], k, n_samples, w);
@@ -396,7 +407,7 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
                 ls = off + __popc(ballot & ((1u << lane) - 1u));
                 s_surv[ls] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));   // passes are < 2^31 samples
             }
-            s_slot[t * 256 + threadIdx.x] = (short)ls;
+            s_slot[(t * 8 + wid) * 33 + lane] = (short)ls;
             __syncthreads();                                      // warp_cnt is rewritten by the next chunk
         }
         const int total = run;
@@ -404,17 +415,15 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
         __syncthreads();
         const int gbase = s_base;
         for (int x = threadIdx.x; x < total; x += 256) surv[gbase + x] = s_surv[x];
+        // sample -> slot map, walked ray-major (64 consecutive depth steps of a ray are 256 contiguous bytes)
 #pragma unroll 1
-        for (int t = 0; t < CULL_T; ++t) {
-            const int ls = s_slot[t * 256 + threadIdx.x];
+        for (int x = threadIdx.x; x < CULL_SPAN; x += 256) {
+            const int rr = rays ? x >> 6 : x & 31, kl = rays ? x & 63 : x >> 5;
+            const int ls = s_slot[kl * 33 + rr];
             if (ls == -2) continue;
-            const long long j = sbase + t * 256 + threadIdx.x;
-            long long i = j;
-            if (n_samples > 0) {
-                const long long g = j / group;
-                const int w = (int)(j - g * group);
-                i = (g * 32 + (w & 31)) * n_samples + (w >> 5);
-            }
+            long long i = sbase + kl * 32 + rr, r;
+            int k;
+            if (rays) cull_locate(cw, kl * 32 + rr, r, k, i);
             surv_of_sample[i] = ls >= 0 ? gbase + ls : -1;
         }
         __syncthreads();
