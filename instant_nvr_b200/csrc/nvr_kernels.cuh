@@ -299,23 +299,26 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
     // U is finite only if some cluster holds >= 4 real vertices, so the four neighbours are real here too
     if (allow_skip && best > NVR_GAP_FACTOR2 * thresh * thresh && U <= NVR_REACH_D2) return KNN_UNFLAGGED;
     U *= 1.00001f;
-    // round -1 holds only the seed (every live lane scans it: its 4th-best is still +inf); rounds 0.. hold the rest
-    for (int cb = -32; cb < ncl; cb += 32) {
+    // the seed first: every live lane's 4th-best is still +inf, so all of them take it
+    nvr_knn_scan(fr.verts + (long long)(c0 + seed) * NVR_CL, p, k);
+    // then rounds of 32 clusters, one per lane.  Inside a round the clusters are taken BEST-FIRST (smallest box-to-box
+    // gap) and the group bound -- no lane needs a cluster whose gap exceeds the LARGEST current 4th-best distance of the
+    // warp (non-negative floats order like their bits) -- is refreshed after every scan, so the few nearest clusters
+    // tighten it and most of the round's other clusters are dropped by one vote without being looked at per lane.
+    for (int cb = 0; cb < ncl; cb += 32) {
         const int c = cb + lane;
-        bool cand = lane == 0;
-        if (cb >= 0) {
-            // group bound, refreshed every round: no lane needs a cluster whose box-to-box gap exceeds the
-            // LARGEST current 4th-best distance of the warp (non-negative floats order like their bits)
+        bool avail = c < ncl && c != seed;                        // this lane's cluster has not been taken yet
+        float gapc = 0.0f;
+        if (avail) gapc = box_gap2(__ldg(fr.cl_lo + c0 + c), __ldg(fr.cl_hi + c0 + c), qlo, qhi) * NVR_PRUNE_SLACK;
+        while (true) {
             const float worst = __uint_as_float(__reduce_max_sync(0xffffffffu, live ? (unsigned int)(k.key[3] >> 32) : 0u));
             const float bound = fminf(U, worst * 1.00001f);
-            cand = false;
-            if (c < ncl && c != seed)
-                cand = !(box_gap2(__ldg(fr.cl_lo + c0 + c), __ldg(fr.cl_hi + c0 + c), qlo, qhi) * NVR_PRUNE_SLACK > bound);
-        }
-        unsigned m = __ballot_sync(0xffffffffu, cand);
-        while (m) {
-            const int cc = cb < 0 ? seed : cb + __ffs(m) - 1;
-            m &= m - 1;
+            const bool cand = avail && !(gapc > bound);
+            // smallest gap among the remaining candidates; the lane index rides in the 5 low mantissa bits
+            const unsigned int sel = __reduce_min_sync(0xffffffffu, cand ? ((__float_as_uint(gapc) & ~31u) | (unsigned)lane) : 0xffffffffu);
+            if (sel == 0xffffffffu) break;
+            const int cc = cb + (int)(sel & 31u);
+            if (lane == (int)(sel & 31u)) avail = false;
             const float lb = nvr_aabb_lb(__ldg(fr.cl_lo + c0 + cc), __ldg(fr.cl_hi + c0 + cc), p);
             const bool need = live && !(lb * NVR_PRUNE_SLACK > nvr_knn_d2(k, 3));
             if (__any_sync(0xffffffffu, need)) nvr_knn_scan(fr.verts + (long long)(c0 + cc) * NVR_CL, p, k);
