@@ -336,7 +336,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     KnnRec* recs = (KnnRec*)w.emb;
     const int far_slot = far_collapse(h, dbg, out_x0) ? (int)w.cap - 1 : -1;
     { StageTimer t(h, st, NVR_STAGE_KNN);
-    if (!(h->cfg.tune & NVR_TUNE_KNN_OCC4))     // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
+    if (h->cfg.tune & NVR_TUNE_KNN_OCC5)        // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
         k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot);
     else
         k_knn<4><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot); }
