@@ -171,7 +171,10 @@ def grid_desc(gp) -> NvrGrid:
     g.n_levels, g.n_feat, g.start_hash = spec.n_levels, spec.n_feat, spec.start_hash
     g.sum_features = int(spec.sum_features)
     g.table_size = spec.T
-    size32 = gp.entries_size.detach().cpu().tolist()           # already fp32-rounded
+    size32 = getattr(gp, "_size32_host", None)                 # frozen buffer: one device->host read per module, not per call
+    if size32 is None or gp._size32_src != (gp.entries_size.data_ptr(), gp.entries_size._version):
+        size32 = gp.entries_size.detach().cpu().tolist()       # already fp32-rounded
+        gp._size32_host, gp._size32_src = size32, (gp.entries_size.data_ptr(), gp.entries_size._version)
     for l in range(spec.n_levels):
         g.res[l], g.size[l], g.dense_off[l] = spec.res[l], size32[l], spec.dense_offsets[l]
     for l in range(spec.n_levels, MAX_LEVELS):

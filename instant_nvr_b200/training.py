@@ -20,6 +20,19 @@ def trainable(net) -> List[Tuple[str, torch.nn.Parameter]]:
     return [(n, p) for n, p in net.named_parameters() if p.requires_grad]
 
 
+def zero_grads(params: Dict[str, torch.Tensor], names: List[str]) -> Dict[str, torch.Tensor]:
+    """Fresh zero-filled gradient buffers for ``names``: ONE allocation and ONE fill launch (the 67 trainable tensors
+    are views of it at 256-byte-aligned offsets) instead of one of each per tensor.  A new buffer every call: autograd
+    takes ownership of what a backward returns (``.grad`` may alias it), so it must not be reused."""
+    offs, total = [], 0
+    for name in names:
+        offs.append(total)
+        total += (params[name].numel() + 63) & ~63
+    ref = params[names[0]]
+    flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
+    return {name: flat[o:o + params[name].numel()].view(params[name].shape) for name, o in zip(names, offs)}
+
+
 class _NetworkTrainFn(torch.autograd.Function):
     """raw (N,4), occ (N,1), resd (Ns,5,3), tocc (Ns,5) [differentiable]; x0 (Ns,5,3), sample_of_slot (Ns) [constants].
     Slot order (compaction order) on this level; the caller re-orders to the reference's sample order."""
@@ -51,8 +64,7 @@ class _NetworkTrainFn(torch.autograd.Function):
             full = torch.zeros((n,) + tail, dtype=torch.float32, device=g.device)
             full[:ns] = g
             return full
-        params = dict(trainable(net))
-        grads = {name: torch.zeros_like(params[name]) for name in ctx.names}
+        grads = zero_grads(dict(trainable(net)), ctx.names)
         eng.train_backward(state, g_raw, slots(d_resd, (5, 3)), slots(d_tocc, (5,)), net, grads)
         ctx.state = None
         return (None, None, None, None) + tuple(grads[name] for name in ctx.names)
@@ -86,8 +98,7 @@ class _DeformerFn(torch.autograd.Function):
     def backward(ctx, d_resd):
         (pts,) = ctx.saved_tensors
         net = ctx.net
-        params = dict(trainable(net))
-        grads = {name: torch.zeros_like(params[name]) for name in ctx.names}
+        grads = zero_grads(dict(trainable(net)), ctx.names)
         net.engine().deformer_backward(pts, d_resd.contiguous(), ctx.batch, net, grads)
         return (None, None, None) + tuple(grads[name] for name in ctx.names)
 

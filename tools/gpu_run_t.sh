@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_training.py -m gpu -q -x --timeout 600 -s > gpurun_out/pytest_train.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_train.log
-tail -40 gpurun_out/pytest_train.log
+timeout 600 python tools/train_breakdown.py > gpurun_out/train_breakdown.log 2>&1; echo "rc=$?"; head -12 gpurun_out/train_breakdown.log; grep -A32 "Self CPU %" gpurun_out/train_breakdown.log | cut -c1-70,130-260 | head -40
