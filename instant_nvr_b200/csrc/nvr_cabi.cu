@@ -330,6 +330,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     const int sm = h->sm_count;
     NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
     { StageTimer t(h, st, NVR_STAGE_CULL);
+    NVR_CHECK(h, cudaMemsetAsync(w.surv_of_sample, 0xFF, (size_t)n * sizeof(int), st));   // -1 = culled; k_cull fills in the survivors
     k_cull<<<grid_for(n, 256 * CULL_T, sm * 8), 256, 0, st>>>(h->fdev, pts, ray_d, near_, far_, n, n_samples, h->cfg.smpl_thresh,
                                                       w.counters, w.surv_of_sample, w.surv); }
     // neighbour records alias the embedding buffer: they are consumed by k_warp before k_embed writes it

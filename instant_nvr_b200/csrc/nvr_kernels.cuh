@@ -353,12 +353,12 @@ __device__ __forceinline__ bool cull_locate(const CullWalk& cw, int local, long 
     return r < cw.n_rays;
 }
 
+// surv_of_sample must be pre-filled with -1 (cudaMemsetAsync 0xFF): only survivors' entries are written here.
 __global__ void __launch_bounds__(256)
 k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray_d,
        const float* __restrict__ near_, const float* __restrict__ far_, long long n, int n_samples,
        float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv) {
     __shared__ float4 s_surv[CULL_SPAN];
-    __shared__ short s_slot[64 * 33];                             // [depth step][ray] (+1 pad): slot in the CTA's run, -1 = culled, -2 = no sample
     __shared__ int warp_cnt[8];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -368,10 +368,16 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
     cw.group = 32u * (unsigned)cw.S;
     cw.n_rays = rays ? n / n_samples : 0;
     const long long n_map = rays ? ((cw.n_rays + 31) / 32) * (long long)cw.group : n;
+    __shared__ CullQuick cq;                                      // uniform: one copy per CTA, broadcast reads
+    const bool quick = fr.dist_cmin != nullptr;
+    if (quick && threadIdx.x == 0) nvr_cull_quick_setup(fr.dist, fr.R, fr.Th, cq);
+    __syncthreads();
     for (long long sbase = (long long)blockIdx.x * CULL_SPAN; sbase < n_map; sbase += (long long)gridDim.x * CULL_SPAN) {
         cw.g0 = sbase / (long long)cw.group;
         cw.w0 = (unsigned)(sbase - cw.g0 * (long long)cw.group);
         int run = 0;                                              // survivors of the earlier chunks (same in every thread)
+        long long r_have = -1;                                    // the ray whose data the registers below hold
+        float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, nr = 0.f, fa = 0.f, qa[3] = {0.f, 0.f, 0.f}, qb[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int t = 0; t < CULL_T; ++t) {
             const int local = t * 256 + threadIdx.x;
@@ -382,21 +388,40 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
             bool keep = false;
             float p[3] = {0.f, 0.f, 0.f};
             if (valid) {
-                float w[3];
+                float w[3], c[3];
+                bool culled = false;
                 if (rays) {
-                    const float o[3] = {pts[r * 3], pts[r * 3 + 1], pts[r * 3 + 2]};
-                    const float d[3] = {ray_d[r * 3], ray_d[r * 3 + 1], ray_d[r * 3 + 2]};
-                    nvr_ray_sample(o, d, near_[r], far_[r], k, n_samples, w);
+                    if (r != r_have) {                            // a thread keeps its ray for the whole span (256 % 32 == 0)
+                        r_have = r;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { o[a] = pts[r * 3 + a]; d[a] = ray_d[r * 3 + a]; }
+                        nr = near_[r]; fa = far_[r];
+                        if (quick) nvr_cull_quick_ray(cq, o, d, qa, qb);
+                    }
+                    if (quick) {
+                        const float tk = nvr_linspace01(k, n_samples);
+                        const float z = nr * (1.0f - tk) + fa * tk;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) c[a] = qa[a] + z * qb[a];
+                        culled = nvr_cull_quick(fr.dist, cq, fr.dist_cmin, c, thresh);
+                    }
+                    if (!culled) nvr_ray_sample(o, d, nr, fa, k, n_samples, w);
                 } else {
                     w[0] = pts[i * 3]; w[1] = pts[i * 3 + 1]; w[2] = pts[i * 3 + 2];
+                    if (quick) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) c[a] = ((w[0] * cq.M[a] + w[1] * cq.M[3 + a]) + w[2] * cq.M[6 + a]) + cq.t[a];
+                        culled = nvr_cull_quick(fr.dist, cq, fr.dist_cmin, c, thresh);
+                    }
                 }
-                nvr_world_to_pose(fr.R, fr.Th, w, p);
-                float c[3];
-                nvr_volume_coords(fr.dist, p, c);
-                if (!(fr.dist_cmin && nvr_cull_early_out(fr.dist, fr.dist_cmin, c, thresh))) {
-                    float pn;
-                    nvr_sample_volume_at(fr.dist, c, 0, 1, &pn);
-                    keep = pn < thresh;                           // inb_part_network_multiassign.py:136
+                if (!culled) {                                    // the reference's arithmetic, bit for bit
+                    nvr_world_to_pose(fr.R, fr.Th, w, p);
+                    nvr_volume_coords(fr.dist, p, c);
+                    if (!(quick && nvr_cull_early_out(fr.dist, fr.dist_cmin, c, thresh))) {
+                        float pn;
+                        nvr_sample_volume_at(fr.dist, c, 0, 1, &pn);
+                        keep = pn < thresh;                       // inb_part_network_multiassign.py:136
+                    }
                 }
             }
             const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -405,29 +430,17 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
             int off = run;
 #pragma unroll
             for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; off += w < wid ? c : 0; run += c; }
-            int ls = valid ? -1 : -2;
-            if (keep) {
-                ls = off + __popc(ballot & ((1u << lane) - 1u));
-                s_surv[ls] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));   // passes are < 2^31 samples
-            }
-            s_slot[(t * 8 + wid) * 33 + lane] = (short)ls;
+            if (keep) s_surv[off + __popc(ballot & ((1u << lane) - 1u))] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));   // passes are < 2^31 samples
             __syncthreads();                                      // warp_cnt is rewritten by the next chunk
         }
         const int total = run;
         if (threadIdx.x == 0) s_base = total ? atomicAdd(&counters[NVR_CTR_SURV], total) : 0;
         __syncthreads();
         const int gbase = s_base;
-        for (int x = threadIdx.x; x < total; x += 256) surv[gbase + x] = s_surv[x];
-        // sample -> slot map, walked ray-major (64 consecutive depth steps of a ray are 256 contiguous bytes)
-#pragma unroll 1
-        for (int x = threadIdx.x; x < CULL_SPAN; x += 256) {
-            const int rr = rays ? x >> 6 : x & 31, kl = rays ? x & 63 : x >> 5;
-            const int ls = s_slot[kl * 33 + rr];
-            if (ls == -2) continue;
-            long long i = sbase + kl * 32 + rr, r;
-            int k;
-            if (rays) cull_locate(cw, kl * 32 + rr, r, k, i);
-            surv_of_sample[i] = ls >= 0 ? gbase + ls : -1;
+        for (int x = threadIdx.x; x < total; x += 256) {
+            const float4 sv = s_surv[x];
+            surv[gbase + x] = sv;
+            surv_of_sample[__float_as_int(sv.w)] = gbase + x;
         }
         __syncthreads();
     }

@@ -290,15 +290,48 @@ NVR_HD bool nvr_cull_early_out(const VolumeDev& v, const float* cmin, const floa
     return m > thresh * NVR_CULL_MARGIN;
 }
 // minimum of a 1-channel volume over the fine indices a coarse cell's lookups can touch
+// (one extra voxel on every side, so that a cell index taken from coordinates that are off by less than a voxel --
+// nvr_cull_quick -- is covered too)
 NVR_HD float nvr_coarse_min(const float* dist, int D, int H, int W, int cz, int cy, int cx) {
     float m = INFINITY;
-    for (int z = cz * NVR_CULL_B; z <= cz * NVR_CULL_B + NVR_CULL_B && z < D; ++z)
-        for (int y = cy * NVR_CULL_B; y <= cy * NVR_CULL_B + NVR_CULL_B && y < H; ++y)
-            for (int x = cx * NVR_CULL_B; x <= cx * NVR_CULL_B + NVR_CULL_B && x < W; ++x) {
+    for (int z = (cz * NVR_CULL_B > 0 ? cz * NVR_CULL_B - 1 : 0); z <= cz * NVR_CULL_B + NVR_CULL_B + 1 && z < D; ++z)
+        for (int y = (cy * NVR_CULL_B > 0 ? cy * NVR_CULL_B - 1 : 0); y <= cy * NVR_CULL_B + NVR_CULL_B + 1 && y < H; ++y)
+            for (int x = (cx * NVR_CULL_B > 0 ? cx * NVR_CULL_B - 1 : 0); x <= cx * NVR_CULL_B + NVR_CULL_B + 1 && x < W; ++x) {
                 const float d = dist[((long long)z * H + y) * W + x];
                 m = (d < m || d != d) ? d : m;                  // a NaN voxel poisons the cell: never early-out on it
             }
     return m;
+}
+
+// Quick conservative cull straight from WORLD coordinates: the chain world -> pose -> normalised -> voxel coordinates
+// is affine, c_a = sum_b w_b M[b][a] + t_a, so one 3x4 map (12 FMAs, no divisions) gives the voxel coordinates to
+// ~1e-4 voxel -- not the reference's bits, but the coarse-minimum grid carries a one-voxel margin, so a sample this
+// test culls is one the exact lookup would cull as well; everything else takes the exact path.  Along a ray the map
+// collapses further to c = A + z B with A = o.M + t, B = d.M.
+struct CullQuick { float M[9]; float t[3]; float cmax[3]; };
+NVR_HD void nvr_cull_quick_setup(const VolumeDev& v, const float* R, const float* Th, CullQuick& q) {
+    const int dims[3] = {v.D, v.H, v.W};
+    for (int a = 0; a < 3; ++a) {
+        const float s = (float)(dims[a] - 1) / (v.bounds[3 + a] - v.bounds[a]);
+        for (int b = 0; b < 3; ++b) q.M[b * 3 + a] = R[b * 3 + a] * s;
+        q.t[a] = -(((Th[0] * R[0 * 3 + a] + Th[1] * R[1 * 3 + a]) + Th[2] * R[2 * 3 + a]) + v.bounds[a]) * s;
+        q.cmax[a] = (float)(dims[a] - 1);
+    }
+}
+NVR_HD void nvr_cull_quick_ray(const CullQuick& q, const float o[3], const float d[3], float A[3], float B[3]) {
+    for (int a = 0; a < 3; ++a) {
+        A[a] = ((o[0] * q.M[0 * 3 + a] + o[1] * q.M[1 * 3 + a]) + o[2] * q.M[2 * 3 + a]) + q.t[a];
+        B[a] = (d[0] * q.M[0 * 3 + a] + d[1] * q.M[1 * 3 + a]) + d[2] * q.M[2 * 3 + a];
+    }
+}
+// c: approximate voxel coordinates (unclamped).  true = certainly culled.  NaN coordinates clamp to 0 here; the exact
+// path culls them too (a NaN lookup is never < thresh).
+NVR_HD bool nvr_cull_quick(const VolumeDev& v, const CullQuick& q, const float* cmin, const float c[3], float thresh) {
+    const int cz = (int)fminf(fmaxf(c[0], 0.0f), q.cmax[0]) / NVR_CULL_B;
+    const int cy = (int)fminf(fmaxf(c[1], 0.0f), q.cmax[1]) / NVR_CULL_B;
+    const int cx = (int)fminf(fmaxf(c[2], 0.0f), q.cmax[2]) / NVR_CULL_B;
+    const float m = cmin[(cz * nvr_coarse_dim(v.H) + cy) * nvr_coarse_dim(v.W) + cx];
+    return m > thresh * NVR_CULL_MARGIN;
 }
 
 // ---------------------------------------------------------------------------------------

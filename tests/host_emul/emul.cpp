@@ -246,6 +246,26 @@ void emul_adam(float* p, const float* g, float* m, float* v, long long n, long l
 }
 // distance cull with and without the coarse-minimum early-out (k_frame_coarse + k_cull): keep[i] = exact decision,
 // early[i] = 1 when the early-out fires (it must then agree with a culled exact decision).
+// quick world-space cull (nvr_cull_quick) next to the exact decision for world points: keep = exact lookup < thresh
+void emul_cull_quick(const float* dist, int D, int H, int W, const float* bounds, const float* R, const float* Th, const float* wpts,
+                     long long n, float thresh, unsigned char* keep, unsigned char* quick) {
+    VolumeDev v{dist, D, H, W, 1, bounds};
+    const int cD = nvr_coarse_dim(D), cH = nvr_coarse_dim(H), cW = nvr_coarse_dim(W);
+    std::vector<float> cmin((size_t)cD * cH * cW);
+    for (int i = 0; i < cD * cH * cW; ++i) cmin[i] = nvr_coarse_min(dist, D, H, W, i / (cH * cW), (i / cW) % cH, i % cW);
+    CullQuick q;
+    nvr_cull_quick_setup(v, R, Th, q);
+    for (long long i = 0; i < n; ++i) {
+        const float* w = wpts + i * 3;
+        float cq[3], p[3], c[3], pn;
+        for (int a = 0; a < 3; ++a) cq[a] = ((w[0] * q.M[a] + w[1] * q.M[3 + a]) + w[2] * q.M[6 + a]) + q.t[a];
+        quick[i] = nvr_cull_quick(v, q, cmin.data(), cq, thresh) ? 1 : 0;
+        nvr_world_to_pose(R, Th, w, p);
+        nvr_volume_coords(v, p, c);
+        nvr_sample_volume_at(v, c, 0, 1, &pn);
+        keep[i] = pn < thresh ? 1 : 0;
+    }
+}
 void emul_cull(const float* dist, int D, int H, int W, const float* bounds, const float* pts, long long n, float thresh,
                unsigned char* keep, unsigned char* early) {
     VolumeDev v{dist, D, H, W, 1, bounds};

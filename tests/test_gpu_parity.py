@@ -293,12 +293,13 @@ def test_far_field_pairs_share_one_evaluation(gpu, gain):
     cfg, gb, net = gpu["cfg"], gpu["gbatch"], gpu["nets"][gain]
     S = cfg.N_samples
     out = {}
-    for tune in (0, 8):
+    for tune in (0, 8, 12):                                   # 12: also no quick / early-out cull (every sample through the exact lookup)
         eng = Engine(cfg, tune=tune)
         eng.bind_params(net)
         rgb, acc, raw = eng.render_rays(gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0], S, want_raw=True, batch=gb)
         out[tune] = (rgb, acc, raw, eng.counters())
     (rgb0, acc0, raw0, c0), (rgb8, acc8, raw8, c8) = out[0], out[8]
+    assert torch.equal(out[12][2], raw8) and out[12][3]["n_survivors"] == c8["n_survivors"] and out[12][3]["n_pairs"] == c8["n_pairs"]
     assert sum(c8["n_far_pairs"]) == 0 and sum(c0["n_far_pairs"]) > 0
     assert c0["n_survivors"] == c8["n_survivors"] > 0
     for p in range(5):
@@ -425,7 +426,7 @@ def test_full_size_properties_c2(full):
     #     the every-pair evaluation (NVR_TUNE_NO_FAR_COLLAPSE) on the same 2.56 M samples, full-size tables
     from instant_nvr_b200.engine import Engine
     c0 = c_perm
-    eng8 = Engine(cfg, tune=8)
+    eng8 = Engine(cfg, tune=12)                               # every pair on its own, every sample through the exact cull lookup
     eng8.bind_params(net)
     rgb_8, acc_8, raw_8 = eng8.render_rays(o[perm], d[perm], n[perm], f[perm], S, want_raw=True, batch=gb)
     c8 = eng8.counters()

@@ -275,3 +275,32 @@ def test_cull_early_out_is_conservative(emul):
     keep, early = torch.zeros(n, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8)
     emul.emul_cull(fp(vol), C.c_int(D), C.c_int(H), C.c_int(W), fp(b), fp(pts), C.c_longlong(n), C.c_float(0.05), fp(keep), fp(early))
     assert not (early.bool() & keep.bool()).any() and keep.any()
+
+
+def test_cull_quick_world_space_is_conservative(emul):
+    """nvr_cull_quick (one affine map from WORLD coordinates to voxel coordinates, coarse-minimum grid with a one-voxel
+    margin) may only cull samples the exact world -> pose -> 8-tap lookup culls too, and should remove most of them."""
+    from instant_nvr_b200.synthetic import make_frame
+    g = torch.Generator().manual_seed(1)
+    for seed in (3, 5):
+        frame = make_frame(seed=seed)
+        dist = frame["pbw"][0, ..., -1].contiguous()
+        D, H, W = dist.shape
+        b, R, Th = frame["pbounds"][0].contiguous(), frame["R"][0].contiguous(), frame["Th"][0].contiguous()
+        lo, hi = b[0], b[1]
+        pose = lo + (hi - lo) * (torch.rand(400000, 3, generator=g) * 1.3 - 0.15)
+        # points exactly on voxel planes and coarse-cell boundaries: where an approximate coordinate may change cell
+        grid = lo + (hi - lo) * (torch.randint(0, max(D, H, W), (50000, 3), generator=g).float()
+                                 / torch.tensor([D - 1.0, H - 1.0, W - 1.0])).clamp(max=1.0)
+        pose = torch.cat([pose, grid, lo[None], hi[None]])
+        wpts = (pose @ R.T + Th).contiguous()                         # world points whose pose-space image is `pose`
+        special = torch.tensor([[float("nan"), 0.0, 0.0], [float("inf"), 0.0, 0.0], [-float("inf"), 1.0, 1.0], [1e30, -1e30, 0.0]])
+        wpts = torch.cat([wpts, special]).contiguous()
+        n = wpts.shape[0]
+        for vol, thresh in ((dist, 0.05), (dist, 0.1), ((0.05 * (1.0 + 3e-6 * torch.randn(D, H, W, generator=g))).contiguous(), 0.05)):
+            keep, quick = torch.zeros(n, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8)
+            emul.emul_cull_quick(fp(vol), C.c_int(D), C.c_int(H), C.c_int(W), fp(b), fp(R), fp(Th), fp(wpts), C.c_longlong(n),
+                                 C.c_float(thresh), fp(keep), fp(quick))
+            assert not (quick.bool() & keep.bool()).any()
+            if vol is dist:
+                assert keep.sum() > 1000 and quick.sum() > 0.55 * (~keep.bool()).sum(), (int(quick.sum()), int((~keep.bool()).sum()))
