@@ -354,7 +354,7 @@ __device__ __forceinline__ bool cull_locate(const CullWalk& cw, int local, long 
 }
 
 // surv_of_sample must be pre-filled with -1 (cudaMemsetAsync 0xFF): only survivors' entries are written here.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray_d,
        const float* __restrict__ near_, const float* __restrict__ far_, long long n, int n_samples,
        float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv) {
@@ -375,12 +375,14 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
     for (long long sbase = (long long)blockIdx.x * CULL_SPAN; sbase < n_map; sbase += (long long)gridDim.x * CULL_SPAN) {
         cw.g0 = sbase / (long long)cw.group;
         cw.w0 = (unsigned)(sbase - cw.g0 * (long long)cw.group);
-        int run = 0;                                              // survivors of the earlier chunks (same in every thread)
+        // warp `wid` owns positions [wid * 256, wid * 256 + 256) of the span -- 8 consecutive depth steps of the 32 rays --
+        // and compacts them into its own 256-record segment of s_surv: no CTA barrier inside the loop
+        int run = 0;                                              // survivors of this warp so far (warp-uniform)
         long long r_have = -1;                                    // the ray whose data the registers below hold
         float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, nr = 0.f, fa = 0.f, qa[3] = {0.f, 0.f, 0.f}, qb[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
         for (int t = 0; t < CULL_T; ++t) {
-            const int local = t * 256 + threadIdx.x;
+            const int local = (wid * CULL_T + t) * 32 + lane;
             long long i = sbase + local, r = 0;                   // i = sample id
             int k = 0;
             bool valid = i < n;
@@ -391,7 +393,7 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
                 float w[3], c[3];
                 bool culled = false;
                 if (rays) {
-                    if (r != r_have) {                            // a thread keeps its ray for the whole span (256 % 32 == 0)
+                    if (r != r_have) {                            // a lane keeps its ray for the whole span (32 | 256)
                         r_have = r;
 #pragma unroll
                         for (int a = 0; a < 3; ++a) { o[a] = pts[r * 3 + a]; d[a] = ray_d[r * 3 + a]; }
@@ -425,24 +427,23 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
                 }
             }
             const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) warp_cnt[wid] = __popc(ballot);
-            __syncthreads();
-            int off = run;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; off += w < wid ? c : 0; run += c; }
-            if (keep) s_surv[off + __popc(ballot & ((1u << lane) - 1u))] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));   // passes are < 2^31 samples
-            __syncthreads();                                      // warp_cnt is rewritten by the next chunk
+            if (keep) s_surv[wid * 256 + run + __popc(ballot & ((1u << lane) - 1u))] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));   // passes are < 2^31 samples
+            run += __popc(ballot);
         }
-        const int total = run;
+        if (lane == 0) warp_cnt[wid] = run;
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; off += w < wid ? c : 0; total += c; }
         if (threadIdx.x == 0) s_base = total ? atomicAdd(&counters[NVR_CTR_SURV], total) : 0;
         __syncthreads();
-        const int gbase = s_base;
-        for (int x = threadIdx.x; x < total; x += 256) {
-            const float4 sv = s_surv[x];
+        const int gbase = s_base + off;
+        for (int x = lane; x < run; x += 32) {                    // each warp appends its own segment
+            const float4 sv = s_surv[wid * 256 + x];
             surv[gbase + x] = sv;
             surv_of_sample[__float_as_int(sv.w)] = gbase + x;
         }
-        __syncthreads();
+        __syncwarp();                                             // the segment is rewritten by this warp only
     }
 }
 
