@@ -69,8 +69,10 @@ NVR_HD F2 nvr_mul2(const F2& a, const F2& b) {                    // FMUL2
 // warp vote on the device (callers are warp-converged), identity in the scalar host build
 #ifdef __CUDA_ARCH__
 #define NVR_ANY(x) __any_sync(0xffffffffu, (x))
+#define NVR_ANY_ACTIVE(x) __any_sync(__activemask(), (x))   // for loops whose tail leaves a warp partially active
 #else
 #define NVR_ANY(x) (x)
+#define NVR_ANY_ACTIVE(x) (x)
 #endif
 
 // Device-side view of one grid (mirrors NvrGrid, plus the Barrett constant for `% T`).
@@ -542,6 +544,9 @@ NVR_HD void nvr_blend_lbs(const int idx[NVR_KNN], const float w[NVR_KNN], const 
 #pragma unroll 2
     for (int j = 0; j < NVR_JOINTS; ++j) {
         const float bj = nvr_blend_joint(idx, w, pbw_part, j);
+        // skinning rows are sparse (<= 4 joints per vertex) and a warp's pairs are neighbours: most joints have zero
+        // weight for every lane, and adding 0 * A_j changes nothing
+        if (!NVR_ANY_ACTIVE(bj != 0.0f)) continue;
         const F2 b2 = {bj, bj};
 #pragma unroll
         for (int e = 0; e < 6; ++e) {
