@@ -1,15 +1,17 @@
 // nvr_kernels.cuh -- the sm_100a kernels of the per-ray hot path.
 //
-//   k_frame_prep   per frame: distance channel of pbw -> compact volume, part vertices -> packed float4
-//   k_cull         sample gen (ray mode) / point fetch, world->pose, distance cull, block compaction
+//   k_frame_prep   per frame: distance channel of pbw -> compact volume; k_frame_coarse: its coarse-minimum grid
+//   k_cull         sample gen (ray mode, depth-major walk) / point fetch, quick world-space cull, world->pose,
+//                  exact distance cull, per-warp compaction in shared memory, one atomic per 2048 positions
 //   k_cluster_verts per frame: balanced KD partition of each part's vertices into clusters + AABBs
-//                  (the KNN acceleration structure)
-//   k_knn          per survivor: 5x exact K=4 NN (group search over the clusters), Gaussian weights,
-//                  per-part append of flagged (sample, part) neighbour records
-//   k_warp         per flagged pair: blend weights, LBS to big pose, deformer -> canonical point + dir
-//   k_embed        THE gather: quad-lane 64-byte row loads of the dense+hashed grids, per-level sums
-//   k_mlp          occ + rgb MLPs on 128-pair tiles (fp32 FFMA register tiles)
-//   k_resolve      arg-max part fusion; per-sample raw/occ and/or per-ray alpha compositing
+//                  (the KNN acceleration structure); k_cluster_apply re-poses it every frame
+//   k_knn          per survivor: 5x exact K=4 NN (group search over the clusters; whole-warp short cuts for far-field
+//                  and certainly-unflagged parts), Gaussian weights, per-part append of flagged (sample, part)
+//                  neighbour records; far-field pairs are answered by one shared pair per part
+//   k_warp         per evaluated pair: blend weights, LBS to big pose, deformer -> canonical point + dir
+//   k_embed        THE gather: two lanes per 64-byte row of the dense+hashed grids (one 256-bit load each), per-level sums
+//   k_mlp          occ + rgb MLPs on 128-pair tiles (fp32 FFMA register tiles; the tcgen05 version is nvr_mlp_tc.cuh)
+//   k_resolve      far-field marker substitution, arg-max part fusion; per-sample raw/occ and/or per-ray alpha compositing
 //
 // No host synchronisation anywhere: list lengths live in device counters, every consumer kernel is
 // a persistent grid-stride loop that reads its trip count from them.
