@@ -175,24 +175,6 @@ __device__ __forceinline__ void tmem_st16_split(uint32_t t_hi, uint32_t t_lo, co
     tmem_st16(t_lo, l);
 }
 
-// Walk `n_chunks` (even) 16-column chunks of this warp's TMEM lanes starting at column chunk c0 of `tcol`, with the
-// load of chunk c + 1 in flight while `body(c, values)` runs on chunk c: the epilogue has 2 warps per scheduler, so
-// the TMEM round trip is only hidden if the warp hides it from itself.
-template <class Body>
-__device__ __forceinline__ void tmem_walk16(uint32_t tcol, int c0, int n_chunks, Body body) {
-    float va[16], vb[16];
-    tmem_ld16(tcol + c0 * 16, va);
-#pragma unroll 1
-    for (int c = c0; c < c0 + n_chunks; c += 2) {
-        tmem_wait_ld();
-        tmem_ld16(tcol + (c + 1) * 16, vb);
-        body(c, va);
-        tmem_wait_ld();
-        if (c + 2 < c0 + n_chunks) tmem_ld16(tcol + (c + 2) * 16, va);
-        body(c + 1, vb);
-    }
-}
-
 // ---- shared memory and TMEM plan ------------------------------------------------------------------
 // A CTA runs TWO tile slots, each with its own 128-pair tile in flight, so one slot's tensor-core GEMMs
 // overlap the other slot's activation epilogue.  Warp w works for slot (w >> 2) & 1 on TMEM lanes
@@ -319,33 +301,22 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
     const bool three = n_rgb == 3;
     uint32_t phase = 0;
 
-    // this thread's input row of the NEXT tile is fetched while the current tile computes (the loads would otherwise sit
-    // exposed at the head of every tile's serial chain)
-    float4 e_in[5], rec_lo, rec_hi;                                 // PairRec = {x, y, z, vx | vy, vz, surv, pad}
-    auto fetch_inputs = [&](int tile) {
-        const int pr = min(tile * 128 + stid, n - 1);
-        const float4* e4 = reinterpret_cast<const float4*>(el + (size_t)pr * NVR_EMB_STRIDE);
-#pragma unroll
-        for (int q = 0; q < 5; ++q) e_in[q] = __ldg(e4 + q);
-        const float4* r4 = reinterpret_cast<const float4*>(pl + pr);
-        rec_lo = __ldg(r4); rec_hi = __ldg(r4 + 1);
-    };
-    if ((int)blockIdx.x * 2 + slot < n_tiles) fetch_inputs(blockIdx.x * 2 + slot);
-
     for (int tile = blockIdx.x * 2 + slot; tile < n_tiles; tile += gridDim.x * 2) {
         const int row = tile * 128 + stid;
+        const int pr = min(row, n - 1);
         int surv;
         // ---- x = [e 19 | pe 27 | 0 0] -> X_hi / X_lo panels (row = stid)
         {
             float x[48];
+            const float4* e4 = reinterpret_cast<const float4*>(el + (size_t)pr * NVR_EMB_STRIDE);
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
-                const float4 t = e_in[q];
+                const float4 t = __ldg(e4 + q);
                 x[q * 4] = t.x; x[q * 4 + 1] = t.y; x[q * 4 + 2] = t.z; x[q * 4 + 3] = t.w;   // x[19] is overwritten below
             }
-            const float v[3] = {rec_lo.w, rec_hi.x, rec_hi.y};
-            surv = __float_as_int(rec_hi.z);
-            if (tile + (int)gridDim.x * 2 < n_tiles) fetch_inputs(tile + gridDim.x * 2);
+            const PairRec rec = pl[pr];
+            surv = rec.surv;
+            const float v[3] = {rec.vx, rec.vy, rec.vz};
             posenc27_doubling(v, x + 19);                           // part_base_network.py:54
             x[46] = 0.0f; x[47] = 0.0f;
 #pragma unroll
@@ -374,14 +345,18 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
         mbar_wait(bar_a, phase); phase ^= 1;
         tc_fence_after();
         float o0 = lead ? sc[0] : 0.0f;
-        tmem_walk16(trow + TC_COL_HHI, half * CPH, CPH, [&](int c, float* h) {
+#pragma unroll 1
+        for (int c = half * CPH; c < half * CPH + CPH; ++c) {
+            float h[16];
+            tmem_ld16(trow + TC_COL_HHI + c * 16, h);
+            tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 h[k] = nvr_softplus_hidden(h[k] + b0[c * 16 + k]);        // MLP.forward :20-22
                 o0 += w1[c * 16 + k] * h[k];
             }
             tmem_st16_split(trow + TC_COL_HHI + c * 16, trow + TC_COL_HLO + c * 16, h);
-        });
+        }
         if (H == 2 && !lead) ex[0] = o0;
         tmem_wait_st();
         tc_fence_before();
@@ -398,11 +373,15 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
         tc_fence_after();
         float r[3] = {lead ? sc[1] : 0.0f, lead ? sc[2] : 0.0f, lead ? sc[3] : 0.0f};
         if (three) {                                                // block-uniform
-            tmem_walk16(trow + TC_COL_D, half * CPH, CPH, [&](int c, float* g) {
+#pragma unroll 1
+            for (int c = half * CPH; c < half * CPH + CPH; ++c) {
+                float g[16];
+                tmem_ld16(trow + TC_COL_D + c * 16, g);
+                tmem_wait_ld();
 #pragma unroll
                 for (int k = 0; k < 16; ++k) g[k] = nvr_softplus_hidden(g[k] + b2[c * 16 + k]);
                 tmem_st16_split(trow + TC_COL_HHI + c * 16, trow + TC_COL_HLO + c * 16, g);
-            });
+            }
             tmem_wait_st();
             tc_fence_before();
             slot_sync<H>(slot);
@@ -417,13 +396,17 @@ k_mlp_tc(const float* __restrict__ blk, int n_rgb, int part, const int* __restri
         }
         const float* bl = three ? b3 : b2;
         // ---- last hidden activation + rgb = sigmoid(W4 g + b4)   (:58), raw = [rgb, occ] (:60)
-        tmem_walk16(trow + TC_COL_D, half * CPH, CPH, [&](int c, float* g) {
+#pragma unroll 1
+        for (int c = half * CPH; c < half * CPH + CPH; ++c) {
+            float g[16];
+            tmem_ld16(trow + TC_COL_D + c * 16, g);
+            tmem_wait_ld();
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const float a = nvr_softplus_hidden(g[k] + bl[c * 16 + k]);
                 r[0] += w4[c * 16 + k] * a; r[1] += w4[64 + c * 16 + k] * a; r[2] += w4[128 + c * 16 + k] * a;
             }
-        });
+        }
         if (H == 2) {                                               // second half hands its partial rgb sums over
             if (!lead) { ex[1] = r[0]; ex[2] = r[1]; ex[3] = r[2]; }
             tc_fence_before();                                      // its TMEM reads precede the next tile's MMAs too
