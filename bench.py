@@ -427,16 +427,14 @@ def main():
     n_embed = max(prof["launches"]["embed"], 1)
     alg_bytes = BYTES_PER_PAIR * pairs
     achieved = alg_bytes / (embed_ms * 1e-3) / 1e9 if embed_ms > 0 else 0.0
-    # one launch over all five parts' pair lists (k_embed_all) unless NVR_TUNE_EMBED_PER_PART: launches per pass tell which
-    embed_kernel = "k_embed_all" if n_embed <= max(prof.get("passes", 0), 1) else "k_embed"
-    roofline = {"bound": "hbm", "kernel": embed_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_embed", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / n_embed, "avg_launch_ms": embed_ms / n_embed,
                 "launches_timed": n_embed,
-                "note": "8192 B per evaluated (sample, part) pair x pairs; duration = CUDA-event sum over every gather launch "
+                "note": "8192 B per flagged (sample, part) pair x pairs; duration = CUDA-event sum over every k_embed launch "
                         "of the timed region (nvr_profile), rank 0"}
     stage_share = {k: (v / sum(prof["ms"].values()) if sum(prof["ms"].values()) else 0.0) for k, v in prof["ms"].items()}
-    traffic, traffic_src = ncu_traffic_per_launch(embed_kernel)
+    traffic, traffic_src = ncu_traffic_per_launch("k_embed")
     roofline["traffic"] = traffic
     roofline["traffic_source"] = traffic_src
     roofline["note"] += ("; the algorithmic figure assumes no reuse, but neighbouring samples share coarse-level rows and pairs of "
@@ -448,7 +446,7 @@ def main():
     n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
     wavefronts = pairs * 16 * 8
     l1_floor_ms = wavefronts / (n_sm * sm_clock) * 1e3
-    roofline_l1 = {"kernel": embed_kernel, "bound": "l1 wavefronts", "wavefronts": wavefronts, "floor_ms": l1_floor_ms, "measured_ms": embed_ms,
+    roofline_l1 = {"kernel": "k_embed", "bound": "l1 wavefronts", "wavefronts": wavefronts, "floor_ms": l1_floor_ms, "measured_ms": embed_ms,
                    "frac": l1_floor_ms / embed_ms if embed_ms > 0 else 0.0,
                    "note": "16 levels x 8 corners x 1 wavefront (one 64 B row = half a 128 B line) per pair at 1 wavefront/clk/SM "
                            f"({n_sm} SMs x {sm_clock / 1e6:.0f} MHz, B300_MICROARCH.md 'L1tex wavefront queue'); the in-situ limit of "

@@ -121,7 +121,6 @@ typedef struct NvrConfig {
 #define NVR_TUNE_WARP_OCC4 1u      /* k_warp without a register cap (127 registers, 4 CTAs/SM) instead of 8 CTAs/SM (<= 64) */
 #define NVR_TUNE_KNN_OCC5 2u       /* k_knn at 5 CTAs/SM (<= 48 registers, spills) instead of 4 CTAs/SM (<= 64) */
 #define NVR_TUNE_NO_CULL_EARLY_OUT 4u  /* cull: always take the 8-tap lookup (disable the coarse-minimum early-out) */
-#define NVR_TUNE_EMBED_PER_PART 16u     /* one gather launch per part instead of one launch over all five pair lists */
 #define NVR_TUNE_NO_FAR_COLLAPSE 8u    /* evaluate every flagged pair on its own: by default the pairs of a part whose Gaussian
                                           weights sum to < 1e-20 (part farther than ~0.73 m: blended transforms ~1e-12, canonical
                                           point = origin to 5e-13 m) share ONE evaluation per part and frame */

@@ -353,34 +353,18 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
         h->launches++;
     }
-    // the gather: one launch over all five pair lists (units of the parts interleaved), unless the pre-summed
-    // inference tables are in use or NVR_TUNE_EMBED_PER_PART asks for one launch per part
-    const bool presum = h->presum_valid && !full_tables;
-    const bool embed_all = !presum && !(h->cfg.tune & NVR_TUNE_EMBED_PER_PART);
-    if (embed_all) {
-        StageTimer t(h, st, NVR_STAGE_EMBED);
-        EmbedAll ea;
-        for (int p = 0; p < NVR_NUM_PARTS; ++p) {
-            ea.g[p] = h->part_grid[p];
-            ea.xb[p] = (const float*)(w.pairs + (long long)p * w.cap);
-            ea.eb[p] = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
-        }
-        k_embed_all<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(ea, w.counters, 8, NVR_EMB_STRIDE);
-    }
     for (int p = 0; p < NVR_NUM_PARTS; ++p) {
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
-        if (!embed_all) {
-            StageTimer t(h, st, NVR_STAGE_EMBED);
-            if (presum) {
-                const float* sd = h->d_presum + h->presum_off[p];
-                k_embed_presum<<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->part_grid[p], sd, sd + dense_rows(h->params.part[p].grid), (const float*)pl, 8,
-                                                                        w.counters + NVR_CTR_PAIR + p, 0, el, NVR_EMB_STRIDE);
-            } else {
-                k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
-                                                                 el, NVR_EMB_STRIDE);
-            }
-        }
+        { StageTimer t(h, st, NVR_STAGE_EMBED);
+        if (h->presum_valid && !full_tables) {
+            const float* sd = h->d_presum + h->presum_off[p];
+            k_embed_presum<<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->part_grid[p], sd, sd + dense_rows(h->params.part[p].grid), (const float*)pl, 8,
+                                                                    w.counters + NVR_CTR_PAIR + p, 0, el, NVR_EMB_STRIDE);
+        } else {
+            k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
+                                                             el, NVR_EMB_STRIDE);
+        } }
         StageTimer t(h, st, NVR_STAGE_MLP);
         if (tc)
             launch_mlp_tc(h, grid_for(n, 256, sm), h->d_mlp_blocks + (size_t)p * TC_BLOCK_FLOATS, h->part_mlp[p].n_rgb, p,
@@ -390,7 +374,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
                                                                           w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
     }
     NVR_CHECK(h, cudaGetLastError());
-    h->launches += 3 + NVR_NUM_PARTS + (embed_all ? 1 : NVR_NUM_PARTS);
+    h->launches += 3 + 2 * NVR_NUM_PARTS;
     h->last_points = n;
     return 0;
 }

@@ -645,13 +645,15 @@ __device__ __forceinline__ void axis_coord(float u, float size, int res, int& i0
     o = f - (float)i0;
 }
 
-// 16 points starting at `base` of one part's list: lane = 2 * point + half
-__device__ __forceinline__ void embed_unit16(const GridDev& g, const float* __restrict__ xb, int xstride, int n, int base,
-                                             float* __restrict__ eb, int emb_stride) {
+__global__ void __launch_bounds__(256, 2)
+k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
+        float* __restrict__ eb, int emb_stride) {
+    const int n = count_dev ? *count_dev : n_imm;
     const int lane = threadIdx.x & 31, half = lane & 1;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool fast_mod = g.T_magic40 != 0;
     const unsigned int T32 = (unsigned int)g.T;
-    {
+    for (int base = warp * 16; base < n; base += n_warps * 16) {
         const int pt = base + (lane >> 1);
         const bool live = pt < n;
         const float* xp = xb + (long long)(live ? pt : n - 1) * xstride;
@@ -709,47 +711,6 @@ __device__ __forceinline__ void embed_unit16(const GridDev& g, const float* __re
             sfeat += __shfl_xor_sync(0xffffffffu, sfeat, 1);                            // :165 sum over the 16 features
             if (live && half == (l & 1)) o[3 + l] = sfeat;
         }
-    }
-}
-
-__global__ void __launch_bounds__(256, 2)
-k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
-        float* __restrict__ eb, int emb_stride) {
-    const int n = count_dev ? *count_dev : n_imm;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int base = warp * 16; base < n; base += n_warps * 16) embed_unit16(g, xb, xstride, n, base, eb, emb_stride);
-}
-
-// All five parts' pair lists in ONE launch.  The unit of work is 16 pairs of one part; the units of all parts form one
-// index space that every warp walks in a fixed pseudo-random order (multiplication by an odd constant modulo a power of
-// two: a bijection), so at any moment the SMs hold a mix of the HBM-bound body-part units (671 MB of hash tables) and the
-// L1-bound units of the small parts -- the two limits overlap instead of following each other -- and the five launch
-// tails become one.
-struct EmbedAll {
-    GridDev g[NVR_PARTS];
-    const float* xb[NVR_PARTS];
-    float* eb[NVR_PARTS];
-};
-__global__ void __launch_bounds__(256, 2)
-k_embed_all(const __grid_constant__ EmbedAll a, const int* __restrict__ counters, int xstride, int emb_stride) {
-    int first[NVR_PARTS + 1];                                     // first unit of every part
-    first[0] = 0;
-#pragma unroll
-    for (int p = 0; p < NVR_PARTS; ++p) first[p + 1] = first[p] + (counters[NVR_CTR_PAIR + p] + 15) / 16;
-    const unsigned int total = (unsigned int)first[NVR_PARTS];
-    if (total == 0) return;
-    unsigned int span = 1;
-    while (span < total) span <<= 1;
-    const unsigned int mult = (unsigned int)(0.6180339887 * (double)span) | 1u;      // odd: u -> u * mult mod span permutes [0, span)
-    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned int s = warp; s < span; s += n_warps) {
-        const unsigned int u = (s * mult) & (span - 1);
-        if (u >= total) continue;
-        int p = 0, f0 = 0;
-#pragma unroll
-        for (int q = 1; q < NVR_PARTS; ++q)
-            if ((int)u >= first[q]) { p = q; f0 = first[q]; }
-        embed_unit16(a.g[p], a.xb[p], xstride, counters[NVR_CTR_PAIR + p], ((int)u - f0) * 16, a.eb[p], emb_stride);
     }
 }
 
