@@ -343,18 +343,6 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
 // order.
 #define CULL_T 8
 #define CULL_SPAN (256 * CULL_T)
-// position inside the walk -> (ray, step, sample id).  g0 / w0: group index and offset of the CTA's first position
-// (one 64-bit division per 2048 positions); everything per position is 32-bit.
-struct CullWalk { long long g0; unsigned w0, group; int S; long long n_rays; };
-__device__ __forceinline__ bool cull_locate(const CullWalk& cw, int local, long long& r, int& k, long long& i) {
-    const unsigned wl = cw.w0 + (unsigned)local;
-    const unsigned q = wl / cw.group, w = wl - q * cw.group;
-    k = (int)(w >> 5);
-    r = (cw.g0 + q) * 32 + (w & 31);
-    i = r * cw.S + k;
-    return r < cw.n_rays;
-}
-
 // surv_of_sample must be pre-filled with -1 (cudaMemsetAsync 0xFF): only survivors' entries are written here.
 __global__ void __launch_bounds__(256, 4)
 k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray_d,

@@ -336,6 +336,20 @@ NVR_HD bool nvr_cull_quick(const VolumeDev& v, const CullQuick& q, const float* 
     return m > thresh * NVR_CULL_MARGIN;
 }
 
+// k_cull's depth-major walk over the samples of a pass (csrc/nvr_kernels.cuh):
+// position inside the walk -> (ray, step, sample id).  g0 / w0: group index and offset of the CTA's first position
+// (one 64-bit division per 2048 positions); everything per position is 32-bit.
+struct CullWalk { long long g0; unsigned w0, group; int S; long long n_rays; };
+NVR_HD bool cull_locate(const CullWalk& cw, int local, long long& r, int& k, long long& i) {
+    const unsigned wl = cw.w0 + (unsigned)local;
+    const unsigned q = wl / cw.group, w = wl - q * cw.group;
+    k = (int)(w >> 5);
+    r = (cw.g0 + q) * 32 + (w & 31);
+    i = r * cw.S + k;
+    return r < cw.n_rays;
+}
+
+
 // ---------------------------------------------------------------------------------------
 // K=4 nearest vertices -> Gaussian blend weights                 blend_utils.py:732-763
 // ---------------------------------------------------------------------------------------

@@ -246,6 +246,29 @@ void emul_adam(float* p, const float* g, float* m, float* v, long long n, long l
 }
 // distance cull with and without the coarse-minimum early-out (k_frame_coarse + k_cull): keep[i] = exact decision,
 // early[i] = 1 when the early-out fires (it must then agree with a culled exact decision).
+// k_cull's walk, position by position exactly as the kernel's CTAs / warps / lanes take them: visits[sample id] += 1
+void emul_cull_walk(long long n_rays, int S, int grid, int* visits, long long* n_positions) {
+    const int SPAN = 2048, T = 8;
+    CullWalk cw;
+    cw.S = S; cw.group = 32u * (unsigned)S; cw.n_rays = n_rays;
+    const long long n_map = ((n_rays + 31) / 32) * (long long)cw.group;
+    long long pos = 0;
+    for (int block = 0; block < grid; ++block)
+        for (long long sbase = (long long)block * SPAN; sbase < n_map; sbase += (long long)grid * SPAN) {
+            cw.g0 = sbase / (long long)cw.group;
+            cw.w0 = (unsigned)(sbase - cw.g0 * (long long)cw.group);
+            for (int wid = 0; wid < 8; ++wid)
+                for (int t = 0; t < T; ++t)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int local = (wid * T + t) * 32 + lane;
+                        long long r, i; int k;
+                        const bool valid = cull_locate(cw, local, r, k, i) && sbase + local < n_map;
+                        ++pos;
+                        if (valid) { if (k < 0 || k >= S || i != r * S + k) visits[0] = -1000000; else visits[i] += 1; }
+                    }
+        }
+    *n_positions = pos;
+}
 // quick world-space cull (nvr_cull_quick) next to the exact decision for world points: keep = exact lookup < thresh
 void emul_cull_quick(const float* dist, int D, int H, int W, const float* bounds, const float* R, const float* Th, const float* wpts,
                      long long n, float thresh, unsigned char* keep, unsigned char* quick) {

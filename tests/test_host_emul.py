@@ -304,3 +304,17 @@ def test_cull_quick_world_space_is_conservative(emul):
             assert not (quick.bool() & keep.bool()).any()
             if vol is dist:
                 assert keep.sum() > 1000 and quick.sum() > 0.55 * (~keep.bool()).sum(), (int(quick.sum()), int((~keep.bool()).sum()))
+
+
+@pytest.mark.parametrize("n_rays,S", [(1, 1), (1, 7), (31, 16), (32, 64), (33, 64), (100, 128), (1000, 3), (4097, 32), (20000, 128),
+                                      (65, 256), (7, 1000)])
+def test_cull_walk_visits_every_sample_once(emul, n_rays, S):
+    """k_cull's depth-major walk (groups of 32 rays, 2048-position spans, 8 depth steps per warp) is a bijection onto the
+    n_rays x S samples for ragged sizes: ray counts that are not multiples of 32, sample counts that do not divide a span."""
+    visits = np.zeros(n_rays * S, dtype=np.int32)
+    npos = C.c_longlong(0)
+    for grid in (1, 3, 148 * 8):
+        visits[:] = 0
+        emul.emul_cull_walk(C.c_longlong(n_rays), C.c_int(S), C.c_int(grid), visits.ctypes.data_as(C.c_void_p), C.byref(npos))
+        assert visits.min() == 1 and visits.max() == 1, (grid, int(visits.min()), int(visits.max()))
+        assert npos.value >= n_rays * S and npos.value < (n_rays + 32) * S + 2048
