@@ -283,14 +283,16 @@ def test_render_host_and_multipass_match(gpu):
     diag("counters_last_pass", **{k: v for k, v in c.items()})
 
 
-@pytest.mark.parametrize("gain", [1.0, 200.0])
-def test_far_field_pairs_share_one_evaluation(gpu, gain):
+@pytest.mark.parametrize("gain,thresh", [(1.0, None), (200.0, None), (200.0, 0.1), (200.0, 0.02)])
+def test_far_field_pairs_share_one_evaluation(gpu, gain, thresh):
     """Default mode answers every flagged pair whose Gaussian weights sum to < 1e-20 (part farther than ~0.73 m) with ONE
     shared zero-weight evaluation per part (csrc/nvr_kernels.cuh NVR_FAR_WSUM); NVR_TUNE_NO_FAR_COLLAPSE evaluates each
     pair on its own, as the reference does.  The canonical points differ by < 5e-13 m, which fp32 absorbs: the two
     modes must agree to 1e-6 on every sample and bit for bit on (nearly) all of them; the pair accounting must add up."""
     from instant_nvr_b200.engine import Engine
     cfg, gb, net = gpu["cfg"], gpu["gbatch"], gpu["nets"][gain]
+    if thresh is not None:                                    # cfg.smpl_thresh of other configs (0.1) and a tight one: the short cuts scale with it
+        cfg = cfg.with_(smpl_thresh=thresh)
     S = cfg.N_samples
     out = {}
     for tune in (0, 8, 12):                                   # 12: also no quick / early-out cull (every sample through the exact lookup)
@@ -307,7 +309,7 @@ def test_far_field_pairs_share_one_evaluation(gpu, gain):
     d = (raw0 - raw8).abs()
     differ = int((d.max(dim=-1).values > 0).sum())
     active = int((raw8[..., 3] > 0).sum())
-    diag("far_collapse", gain=gain, far_pairs=c0["n_far_pairs"], evaluated=c0["n_pairs"], flagged=c8["n_pairs"],
+    diag("far_collapse", gain=gain, thresh=cfg.smpl_thresh, far_pairs=c0["n_far_pairs"], evaluated=c0["n_pairs"], flagged=c8["n_pairs"],
          max_abs=d.max().item(), samples_not_bitwise_equal=differ, active=active,
          rgb_max_abs=(rgb0 - rgb8).abs().max().item())
     assert d.max().item() <= 1e-6 and differ <= max(2, active // 1000)

@@ -139,3 +139,35 @@ def test_render_from_device_prepared_frame():
     bad = ((raw - rraw).abs().max(dim=-1).values > 1e-4).sum().item()
     assert bad <= max(2, n_active // 500), f"{bad} of {n_active} active samples differ"
     assert O.psnr(out["rgb_map"].cpu(), ref["rgb_map"]) > 50.0
+
+
+def test_error_paths():
+    """Bad arguments come back as error codes / exceptions, never a crash: parents out of order, wrong sizes, missing
+    workspace."""
+    import ctypes as C
+    from instant_nvr_b200 import cabi
+    from instant_nvr_b200.optimizer import aux_handle
+    from instant_nvr_b200.smpl_frame import SmplSubject, _pose_struct, prepare_frame
+    from instant_nvr_b200.synthetic import make_subject
+    sub = make_subject(3, n_verts=500)
+    with pytest.raises(ValueError):
+        SmplSubject(sub["joints"], sub["parents"], sub["weights"][:, :23], sub["tpose"])
+    subject = SmplSubject(sub["joints"], sub["parents"], sub["weights"], sub["tpose"])
+    with pytest.raises(ValueError):
+        prepare_frame(subject, sub["wxyz"], sub["Rh"], sub["Th"], sub["poses"][:60])
+    out = prepare_frame(subject, sub["wxyz"], sub["Rh"], sub["Th"], sub["poses"], volume=False)      # a 500-vertex body works too
+    assert "pbw" not in out and torch.isfinite(out["A"]).all() and out["part_pts"].shape[2] == subject.maxlen
+    lib, h = aux_handle(torch.device("cuda"))
+    bad = sub["parents"].copy()
+    bad[3] = 7                                                    # a child before its parent
+    pose = _pose_struct(sub["Rh"], sub["Th"], sub["poses"], np.zeros(72), sub["joints"], bad)
+    f = torch.empty(64, device="cuda")
+    o = cabi.NvrSmplOut(f.data_ptr(), f.data_ptr(), None, None, f.data_ptr(), None, None, None)
+    ws = torch.empty(4096, dtype=torch.uint8, device="cuda")
+    rc = lib.nvr_smpl_pose_frame(h, C.byref(pose), f.data_ptr(), 1, None, 0, 0.05, C.byref(o), ws.data_ptr(), ws.numel(), None)
+    assert rc != 0 and b"parents" in lib.nvr_last_error(h)
+    pose = _pose_struct(sub["Rh"], sub["Th"], sub["poses"], np.zeros(72), sub["joints"], sub["parents"])
+    rc = lib.nvr_smpl_pose_frame(h, C.byref(pose), f.data_ptr(), 1, None, 0, 0.05, C.byref(o), None, 0, None)
+    assert rc != 0 and b"workspace" in lib.nvr_last_error(h)
+    dims, origin = (C.c_int32 * 3)(), (C.c_double * 3)()
+    assert lib.nvr_smpl_volume_dims(h, None, dims, origin, None) != 0
