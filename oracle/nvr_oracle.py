@@ -363,6 +363,47 @@ def render(sd, batch, n_samples: int, smpl_thresh: float, chunk: int = 4096, wan
     return ret
 
 
+def render_train(sd, batch, n_samples: int, smpl_thresh: float, use_pair_reg: bool = True,
+                 use_reg_distortion: bool = True, pair_noise: Optional[torch.Tensor] = None):
+    """Renderer.render with ``net.training`` and cfg.perturb == 0 (inb_renderer.py:53-125, 204-239; one chunk) on top of
+    Network.forward's training outputs (inb_part_network_multiassign.py:161-165).  Plain torch math: ``backward()`` on the
+    result is the reference's gradient flow when ``sd`` holds leaf tensors with requires_grad.
+
+    Returns the reference's keys: rgb_map (1,R,3), acc_map (1,R), raw (1,R*S,4), occ (1,R*S,1), resd (1,M,5,3),
+    tpts (1,5M,3), tocc (1,5M,1), oresd (1,2K,3) [pair regulariser, :78-94], reg_distortion_loss (1,R) [:96-103].
+    ``pair_noise`` (K,3) stands for the ``torch.rand_like`` draw of compute_val_pair_around_range
+    (inb_part_network_multiassign.py:40); when None it is drawn here from the global generator, as the reference does."""
+    b = strip_batch(batch)
+    pts, z = sample_along_rays(b["ray_o"], b["ray_d"], b["near"], b["far"], n_samples)           # :15-31, perturb 0
+    R, S = pts.shape[:2]
+    vd = b["ray_d"][:, None].expand(R, S, 3).reshape(-1, 3)
+    raw, occ, st = network_forward(sd, pts.reshape(-1, 3), vd, b, smpl_thresh, want_stages=True)
+    M = st["pind"].shape[0]
+    ret = {"raw": raw[None], "occ": occ[None], "resd": st["resd"][None], "tpts": st["bigpose"].reshape(1, -1, 3),
+           "tocc": st["raws"][..., 3].reshape(1, -1, 1)}                                        # multiassign :161-165
+    weights, rgb_map, acc_map = composite(raw.reshape(R, S, 4))                                  # :69-72
+    if use_pair_reg:                                                                             # :78-94
+        tocc = ret["tocc"].view(-1)
+        reg = ((tocc - 0.5).abs() < 0.02).nonzero(as_tuple=True)[0]
+        if reg.numel():
+            reg_tpts = ret["tpts"].view(-1, 3)[reg]
+            reg_resd = ret["resd"].view(-1, 3)[reg]
+            noise = torch.rand_like(reg_tpts) if pair_noise is None else pair_noise
+            neighbor = reg_tpts + (noise - 0.5) * 0.01                                           # multiassign :40
+            nei = deformer(sd, neighbor, b["tuv"], b["tbounds"], b["frame_dim"])                  # Network.resd :122-124
+            ret["oresd"] = torch.cat([reg_resd, nei], dim=0)[None]                                # :45-46
+        else:
+            ret["oresd"] = raw.new_zeros(1, 0, 3)
+    if use_reg_distortion:                                                                       # :96-103
+        ww = weights.reshape(R, S, 1) * weights.reshape(R, 1, S)
+        nxt = torch.cat([z[:, 1:], z[:, -1:]], dim=-1)
+        mid = (z + nxt) / 2
+        diff = torch.abs(mid.reshape(R, S, 1) - mid.reshape(R, 1, S))
+        ret["reg_distortion_loss"] = (ww * diff).sum(dim=-1).sum(dim=-1)[None]
+    ret.update({"rgb_map": rgb_map[None], "acc_map": acc_map[None]})
+    return ret
+
+
 def psnr(img_pred, img_gt) -> float:
     """lib/evaluators/if_nerf.py:27-30: -10*ln(mse)/ln(10)."""
     mse = torch.mean((img_pred - img_gt) ** 2)

@@ -156,6 +156,8 @@ def test_render_train_step(setup):
         for k in ("rgb_map", "acc_map", "raw", "resd", "tpts", "tocc", "oresd", "reg_distortion_loss"):
             assert k in ret, k
         assert ret["rgb_map"].shape == target.shape and ret["reg_distortion_loss"].shape == (1, target.shape[1])
+        # the reference's Renderer flattens resd to (1, 5N', 3) (inb_renderer.py:134-136); Network.forward keeps (1, N', 5, 3)
+        assert ret["resd"].shape == ret["tpts"].shape and ret["tocc"].shape == ret["tpts"].shape[:2] + (1,)
         img = ((ret["rgb_map"] - target) ** 2).mean()
         reg = 0.1 * ret["reg_distortion_loss"].mean() + 0.1 * torch.norm(ret["resd"], dim=2).mean()
         if ret["oresd"].numel():
