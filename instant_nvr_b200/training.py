@@ -174,7 +174,7 @@ def render_train(renderer, batch: Dict, epoch: int = -1) -> Dict[str, torch.Tens
         diff = torch.abs(mid.reshape(n_pixel, S, 1) - mid.reshape(n_pixel, 1, S))
         ret["reg_distortion_loss"] = (ww * diff).sum(dim=-1).sum(dim=-1)[None]
     ret.update({"rgb_map": rgb_map[None], "acc_map": acc_map[None], "raw": raw.reshape(1, -1, 4)})
-    ret["resd"] = ret["resd"].reshape(n_batch, -1, 3)                                           # :134-136: (1, 5N', 3) out of the renderer
+    ret["resd"] = ret["resd"].reshape(n_batch, ret["tpts"].shape[1], 3)                         # :134-136: (1, 5N', 3) out of the renderer
     if cfg.use_freespace_loss:                                                                  # :118-121
         ret["freespace_occupancy"] = raw[..., 3][batch["occupancy"][0] == 0][None]
     return ret
