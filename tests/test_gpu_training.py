@@ -197,3 +197,32 @@ def test_render_train_step(setup):
     net.load_state_dict(saved)
     print("[train] image loss over 4 gradient steps:", losses)
     assert all(b < a for a, b in zip(losses, losses[1:]))
+
+
+def test_render_train_outputs_match_oracle(setup):
+    """Renderer.render in training mode (perturb 0) against the oracle's render_train, which tests/test_oracle_train_golden.py
+    pins to the reference's own training forward: every output that does not depend on the pair regulariser's random
+    neighbour draw (the first half of `oresd` is the gathered `resd`, the second half the deformer at jittered points)."""
+    from instant_nvr_b200.renderer import Renderer
+    cfg, net, sd, frame, rays, gb = setup["cfg"], setup["net"], setup["sd"], setup["frame"], setup["rays"], setup["gbatch"]
+    ref = O.render_train(sd, {**frame, **rays}, cfg.N_samples, cfg.smpl_thresh, use_pair_reg=True, use_reg_distortion=True)
+    net.train()
+    try:
+        with torch.no_grad():
+            ret = Renderer(net).render(dict(gb))
+    finally:
+        net.eval()
+    M5 = ref["tpts"].shape[1]
+    assert ret["resd"].shape == (1, M5, 3) and ret["tpts"].shape == (1, M5, 3) and ret["tocc"].shape == (1, M5, 1)
+    assert (ret["resd"].cpu() - ref["resd"].reshape(1, -1, 3)).abs().max() < 1e-5
+    assert (ret["tocc"].cpu() - ref["tocc"]).abs().max() < 1e-3
+    flag = ref["tocc"].reshape(-1) > 0
+    assert (ret["tpts"].cpu() - ref["tpts"])[0][flag].abs().max() < 1e-4
+    assert (ret["raw"].cpu() - ref["raw"]).abs().max() < 1e-3
+    assert (ret["rgb_map"].cpu() - ref["rgb_map"]).abs().max() < 1e-3 and (ret["acc_map"].cpu() - ref["acc_map"]).abs().max() < 1e-3
+    d, dr = ret["reg_distortion_loss"].cpu(), ref["reg_distortion_loss"]
+    assert d.shape == dr.shape and (d - dr).abs().max() <= 1e-3 * max(dr.abs().max().item(), 1e-6)
+    K = ref["oresd"].shape[1] // 2
+    assert ret["oresd"].shape[1] == 2 * K                          # same pairs selected (|tocc - 0.5| < 0.02) ...
+    if K:
+        assert (ret["oresd"][:, :K].cpu() - ref["oresd"][:, :K]).abs().max() < 1e-5     # ... and the same gathered residuals
