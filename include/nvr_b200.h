@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 7
+#define NVR_ABI_VERSION 8
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -124,6 +124,15 @@ typedef struct NvrConfig {
 #define NVR_TUNE_NO_FAR_COLLAPSE 8u    /* evaluate every flagged pair on its own: by default the pairs of a part whose Gaussian
                                           weights sum to < 1e-20 (part farther than ~0.73 m: blended transforms ~1e-12, canonical
                                           point = origin to 5e-13 m) share ONE evaluation per part and frame */
+#define NVR_TUNE_DENSE_A1 16u          /* MEASUREMENT variant of SURVEY.md section 8(d) ("a = 1"): the distance cull keeps every sample
+                                          and every sample is flagged in exactly ONE part (the part with the smallest weighted
+                                          neighbour distance, first on ties), so (sample, part) pairs == samples whatever the input.
+                                          Not the reference's semantics; bench.py's `dense_a1` line only */
+#define NVR_TUNE_NO_LEVEL_MAJOR 64u     /* gather every part in ONE launch over all 16 levels.  By default a part whose tables are
+                                          several times the L2 (body: 724 MB) is gathered level-major, one launch per <= 72 MB slice of
+                                          its tables, so each row comes from HBM once instead of ~6x (identical results) */
+#define NVR_TUNE_SERIAL 32u            /* one stream, no CUDA graph: every launch of a pass back to back on the caller's stream
+                                          (what the per-stage CUDA-event timing of nvr_profile needs; nvr_profile(h, 1) implies it) */
 
 /* Device-side work counters of the most recent pass (diagnostics / benchmark accounting). */
 typedef struct NvrCounters {
@@ -343,9 +352,18 @@ typedef struct NvrStageProfile {
     int64_t survivors;                    /* summed over the profiled passes */
     int64_t pairs[NVR_NUM_PARTS];         /* evaluated pairs (what the gather and the MLPs processed) */
     int64_t far_pairs[NVR_NUM_PARTS];     /* pairs answered by the shared far-field pair */
+    double embed_part_ms[NVR_NUM_PARTS];  /* NVR_STAGE_EMBED / NVR_STAGE_MLP split by part (one launch per part and pass) */
+    double mlp_part_ms[NVR_NUM_PARTS];
 } NvrStageProfile;
 int nvr_profile(NvrHandle h, int32_t enable);
 int nvr_profile_read(NvrHandle h, NvrStageProfile* out);
+
+/* Measurement aid for the gather's roofline (bench.py): how many DISTINCT 32-byte sectors of each part's dense + hash
+ * tables the pair lists of the most recent pass touch (16 levels x 8 corners x 2 sectors per pair, duplicates counted
+ * once) -- the compulsory table traffic of that pass, against SURVEY.md 8(d)'s no-reuse figure of 8192 B per pair.
+ * Re-walks the pair lists left in `workspace` by the last single-pass nvr_query_points / nvr_render_rays call with the
+ * gather's own index arithmetic, marking a bitmap; synchronises `stream`.  unique_sectors_host: 5 int64. */
+int nvr_gather_footprint(NvrHandle h, void* workspace, size_t ws_bytes, int64_t* unique_sectors_host, void* stream);
 
 /* Copies the device counters of the last pass to the host (synchronises `stream`). */
 int nvr_read_counters(NvrHandle h, NvrCounters* out, void* stream);

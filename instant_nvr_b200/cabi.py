@@ -12,7 +12,7 @@ from typing import Optional
 
 MAX_LEVELS = 16
 NUM_PARTS = 5
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnvr_b200.so")
@@ -69,7 +69,8 @@ class NvrCounters(C.Structure):
 
 class NvrStageProfile(C.Structure):
     _fields_ = [("ms", C.c_double * 7), ("launches", C.c_int64 * 7), ("passes", C.c_int64), ("survivors", C.c_int64),
-                ("pairs", C.c_int64 * NUM_PARTS), ("far_pairs", C.c_int64 * NUM_PARTS)]
+                ("pairs", C.c_int64 * NUM_PARTS), ("far_pairs", C.c_int64 * NUM_PARTS),
+                ("embed_part_ms", C.c_double * NUM_PARTS), ("mlp_part_ms", C.c_double * NUM_PARTS)]
 
 
 class NvrAdamTensor(C.Structure):
@@ -134,6 +135,7 @@ SYMBOLS = {
     "nvr_smpl_volume_dims": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p]),
     "nvr_smpl_bweights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                     C.c_void_p, C.c_void_p]),
+    "nvr_gather_footprint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.c_void_p]),
     "nvr_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "nvr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(NvrStageProfile)]),
     "nvr_read_counters": (C.c_int, [C.c_void_p, C.POINTER(NvrCounters), C.c_void_p]),

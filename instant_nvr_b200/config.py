@@ -233,4 +233,7 @@ class PathConfig:
         )
         if cfg.part3 or cfg.part6 or cfg.part_deform:
             raise NotImplementedError("cfg.part3 / part6 / part_deform are outside the inb hot path")
+        if bool(getattr(cfg, "use_occ_loss", False)):
+            # inb_renderer.py:122-129 indexes `obj_occ.shape[1]` of a 1-D tensor: the reference itself raises with this flag
+            raise NotImplementedError("cfg.use_occ_loss ('obj_occupancy', inb_renderer.py:122-129) is not implemented")
         return out

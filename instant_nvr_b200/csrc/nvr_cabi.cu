@@ -48,7 +48,7 @@ struct NvrEngine {
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
-    struct Span { int stage; size_t e0, e1; };
+    struct Span { int stage; int part; size_t e0, e1; };
     std::vector<Span> spans;
     int* h_pass_counters = nullptr;         // pinned [PROF_MAX_PASSES][NVR_CTR_WORDS]
     int n_pass_snap = 0;
@@ -56,8 +56,8 @@ struct NvrEngine {
 static const int PROF_MAX_PASSES = 8192;
 
 struct StageTimer {                         // RAII: records an event pair on `st` when profiling is on
-    NvrEngine* h; cudaStream_t st; int stage; size_t e0 = 0; bool on;
-    StageTimer(NvrEngine* h_, cudaStream_t st_, int stage_) : h(h_), st(st_), stage(stage_), on(h_->profiling) {
+    NvrEngine* h; cudaStream_t st; int stage; int part; size_t e0 = 0; bool on;
+    StageTimer(NvrEngine* h_, cudaStream_t st_, int stage_, int part_ = -1) : h(h_), st(st_), stage(stage_), part(part_), on(h_->profiling) {
         if (!on) return;
         if (h->ev_used + 2 > h->ev_pool.size()) {
             for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
@@ -68,7 +68,7 @@ struct StageTimer {                         // RAII: records an event pair on `s
     ~StageTimer() {
         if (!on) return;
         cudaEventRecord(h->ev_pool[e0 + 1], st);
-        h->spans.push_back({stage, e0, e0 + 1});
+        h->spans.push_back({stage, part, e0, e0 + 1});
     }
 };
 
@@ -306,6 +306,28 @@ static int grid_for(long long items, int per_block, int max_blocks) {
     return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
 }
 
+// Level ranges one part's gather is launched in.  A part whose tables fit the L2 is ONE launch over all levels.  A part
+// whose tables do not (body: 10 hashed levels x 67 MB) would re-read them from HBM several times over -- its pairs arrive
+// in image order, every level's rows are hit at random, and the working set of all levels together is 5x the L2 (ncu r1l:
+// 4.5 GB of DRAM reads for 0.72 GB of tables) -- so it is gathered level-major: consecutive levels are grouped into
+// slices of at most L2_SLICE_BYTES and each slice is one sweep over the pair list, its rows L2-resident for the sweep.
+static const long long L2_SLICE_BYTES = 72ll << 20;
+static const long long L2_SPLIT_ABOVE_BYTES = 384ll << 20;   // ~3x the 126 MB L2 (leg: 290 MB, DRAM traffic already ~1.5x its tables)
+static int embed_plan(const NvrEngine* h, int p, int begin[NVR_MAX_LEVELS], int end[NVR_MAX_LEVELS]) {
+    const NvrGrid& g = h->params.part[p].grid;
+    const long long total = (dense_rows(g) + hash_rows(g)) * 64;
+    if ((h->cfg.tune & NVR_TUNE_NO_LEVEL_MAJOR) || total <= L2_SPLIT_ABOVE_BYTES) { begin[0] = 0; end[0] = g.n_levels; return 1; }
+    int n = 0, lb = 0;
+    long long acc = 0;
+    for (int l = 0; l < g.n_levels; ++l) {
+        const long long bytes = (l < g.start_hash ? (long long)g.res[l] * g.res[l] * g.res[l] : g.table_size) * 64;
+        if (l > lb && acc + bytes > L2_SLICE_BYTES) { begin[n] = lb; end[n] = l; ++n; lb = l; acc = 0; }
+        acc += bytes;
+    }
+    begin[n] = lb; end[n] = g.n_levels;
+    return n + 1;
+}
+
 // tensor-core part MLPs over one part's pair list; mlp_mode 1: one epilogue warpgroup per tile slot, 2: two
 static void launch_mlp_tc(NvrEngine* h, int grid, const float* blk, int n_rgb, int part, const int* count, const PairRec* pl,
                           const float* el, float4* raws, int out_stride, cudaStream_t st) {
@@ -319,7 +341,7 @@ static void launch_mlp_tc(NvrEngine* h, int grid, const float* blk, int n_rgb, i
 // Far-field pairs share one evaluation per part (NVR_FAR_WSUM) unless the caller needs every pair's own record
 // (per-stage debug output, training) or NVR_TUNE_NO_FAR_COLLAPSE is set.
 static bool far_collapse(const NvrEngine* h, const float* dbg, const float* out_x0) {
-    return !(h->cfg.tune & NVR_TUNE_NO_FAR_COLLAPSE) && !dbg && !out_x0;
+    return !(h->cfg.tune & (NVR_TUNE_NO_FAR_COLLAPSE | NVR_TUNE_DENSE_A1)) && !dbg && !out_x0;
 }
 static const float4* far_raws(const NvrEngine* h, const Workspace& w, bool on) {
     return on ? w.raws + (w.cap - 1) * NVR_NUM_PARTS : nullptr;
@@ -328,16 +350,19 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
                     const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
                     float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr, bool full_tables = false) {
     const int sm = h->sm_count;
+    const bool dense_a1 = (h->cfg.tune & NVR_TUNE_DENSE_A1) && !dbg && !out_x0;   // measurement variant (a = 1)
     NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
     { StageTimer t(h, st, NVR_STAGE_CULL);
     NVR_CHECK(h, cudaMemsetAsync(w.surv_of_sample, 0xFF, (size_t)n * sizeof(int), st));   // -1 = culled; k_cull fills in the survivors
     k_cull<<<grid_for(n, 256 * CULL_T, sm * 8), 256, 0, st>>>(h->fdev, pts, ray_d, near_, far_, n, n_samples, h->cfg.smpl_thresh,
-                                                      w.counters, w.surv_of_sample, w.surv); }
+                                                      w.counters, w.surv_of_sample, w.surv, dense_a1 ? 1 : 0); }
     // neighbour records alias the embedding buffer: they are consumed by k_warp before k_embed writes it
     KnnRec* recs = (KnnRec*)w.emb;
     const int far_slot = far_collapse(h, dbg, out_x0) ? (int)w.cap - 1 : -1;
     { StageTimer t(h, st, NVR_STAGE_KNN);
-    if (h->cfg.tune & NVR_TUNE_KNN_OCC5)        // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
+    if (dense_a1)
+        k_knn<4, true><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, nullptr, -1);
+    else if (h->cfg.tune & NVR_TUNE_KNN_OCC5)   // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
         k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot);
     else
         k_knn<4><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot); }
@@ -356,16 +381,20 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     for (int p = 0; p < NVR_NUM_PARTS; ++p) {
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
-        { StageTimer t(h, st, NVR_STAGE_EMBED);
+        { StageTimer t(h, st, NVR_STAGE_EMBED, p);
         if (h->presum_valid && !full_tables) {
             const float* sd = h->d_presum + h->presum_off[p];
             k_embed_presum<<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->part_grid[p], sd, sd + dense_rows(h->params.part[p].grid), (const float*)pl, 8,
                                                                     w.counters + NVR_CTR_PAIR + p, 0, el, NVR_EMB_STRIDE);
         } else {
-            k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
-                                                             el, NVR_EMB_STRIDE);
+            int lb[NVR_MAX_LEVELS], le[NVR_MAX_LEVELS];
+            const int n_slices = embed_plan(h, p, lb, le);
+            for (int i = 0; i < n_slices; ++i)
+                k_embed<<<grid_for(n, 128, sm * 2), 256, 0, st>>>(h->part_grid[p], (const float*)pl, 8, w.counters + NVR_CTR_PAIR + p, 0,
+                                                                 el, NVR_EMB_STRIDE, lb[i], le[i]);
+            h->launches += n_slices - 1;
         } }
-        StageTimer t(h, st, NVR_STAGE_MLP);
+        StageTimer t(h, st, NVR_STAGE_MLP, p);
         if (tc)
             launch_mlp_tc(h, grid_for(n, 256, sm), h->d_mlp_blocks + (size_t)p * TC_BLOCK_FLOATS, h->part_mlp[p].n_rgb, p,
                           w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS, st);
@@ -485,7 +514,8 @@ extern "C" int nvr_embed_part(NvrHandle h, int32_t part, const float* xyz, int64
     if (n == 0) return 0;
     if (n >= (1ll << 31)) return fail(h, "nvr_embed_part: n must be < 2^31");
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
-    k_embed<<<grid_for(n, 128, h->sm_count * 2), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19);
+    k_embed<<<grid_for(n, 128, h->sm_count * 2), 256, 0, (cudaStream_t)stream_>>>(h->part_grid[part], xyz, 3, nullptr, (int)n, out, 19, 0,
+                                                                                  h->params.part[part].grid.n_levels);
     NVR_CHECK(h, cudaGetLastError());
     h->launches++;
     return 0;
@@ -866,6 +896,42 @@ extern "C" int nvr_smpl_bweights(NvrHandle h, const void* workspace, int32_t n_v
     return 0;
 }
 
+// ---- gather footprint (measurement aid) ----------------------------------------------------------------------
+extern "C" int nvr_gather_footprint(NvrHandle h, void* workspace, size_t ws_bytes, int64_t* unique_sectors_host, void* stream_) {
+    if (int rc = ready(h, "nvr_gather_footprint")) return rc;
+    if (!unique_sectors_host) return fail(h, "nvr_gather_footprint: null argument");
+    Workspace w;
+    if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_gather_footprint: not a pass workspace");
+    cudaStream_t st = (cudaStream_t)stream_;
+    size_t max_words = 0;
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) {
+        const NvrGrid& g = h->params.part[p].grid;
+        max_words = std::max(max_words, (size_t)((2 * (dense_rows(g) + hash_rows(g)) + 31) / 32));
+    }
+    unsigned int* bitmap = nullptr;
+    unsigned long long* d_out = nullptr;
+    NVR_CHECK(h, cudaMalloc(&bitmap, max_words * sizeof(unsigned int)));
+    if (cudaMalloc(&d_out, NVR_NUM_PARTS * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(bitmap); return fail(h, "nvr_gather_footprint: out of memory"); }
+    cudaMemsetAsync(d_out, 0, NVR_NUM_PARTS * sizeof(unsigned long long), st);
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) {
+        const NvrGrid& g = h->params.part[p].grid;
+        const size_t words = (size_t)((2 * (dense_rows(g) + hash_rows(g)) + 31) / 32);
+        cudaMemsetAsync(bitmap, 0, words * sizeof(unsigned int), st);
+        k_embed_footprint<<<h->sm_count * 8, 256, 0, st>>>(h->part_grid[p], (const float*)(w.pairs + (long long)p * w.cap), 8,
+                                                           w.counters + NVR_CTR_PAIR + p, bitmap, 2ull * (unsigned long long)dense_rows(g));
+        k_popcount_words<<<h->sm_count * 4, 256, 0, st>>>(bitmap, (long long)words, d_out + p);
+    }
+    unsigned long long host[NVR_NUM_PARTS];
+    cudaError_t e = cudaMemcpyAsync(host, d_out, sizeof(host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(bitmap); cudaFree(d_out);
+    if (e != cudaSuccess) { h->err = std::string("nvr_gather_footprint: ") + cudaGetErrorString(e); return 2; }
+    for (int p = 0; p < NVR_NUM_PARTS; ++p) unique_sectors_host[p] = (int64_t)host[p];
+    h->launches += 2 * NVR_NUM_PARTS;
+    return 0;
+}
+
 extern "C" int nvr_profile(NvrHandle h, int32_t enable) {
     if (!h) return 1;
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
@@ -886,6 +952,8 @@ extern "C" int nvr_profile_read(NvrHandle h, NvrStageProfile* out) {
         NVR_CHECK(h, cudaEventElapsedTime(&ms, h->ev_pool[sp.e0], h->ev_pool[sp.e1]));
         out->ms[sp.stage] += ms;
         out->launches[sp.stage]++;
+        if (sp.part >= 0 && sp.stage == NVR_STAGE_EMBED) out->embed_part_ms[sp.part] += ms;
+        if (sp.part >= 0 && sp.stage == NVR_STAGE_MLP) out->mlp_part_ms[sp.part] += ms;
     }
     out->passes = h->n_pass_snap;
     for (int i = 0; i < h->n_pass_snap; ++i) {

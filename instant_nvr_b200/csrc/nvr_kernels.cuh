@@ -347,7 +347,8 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
 __global__ void __launch_bounds__(256, 4)
 k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray_d,
        const float* __restrict__ near_, const float* __restrict__ far_, long long n, int n_samples,
-       float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv) {
+       float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv, int keep_all) {
+    // keep_all (NVR_TUNE_DENSE_A1, measurement variant): every valid sample survives, whatever its distance
     __shared__ float4 s_surv[CULL_SPAN];
     __shared__ int warp_cnt[8];
     __shared__ int s_base;
@@ -359,7 +360,7 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
     cw.n_rays = rays ? n / n_samples : 0;
     const long long n_map = rays ? ((cw.n_rays + 31) / 32) * (long long)cw.group : n;
     __shared__ CullQuick cq;                                      // uniform: one copy per CTA, broadcast reads
-    const bool quick = fr.dist_cmin != nullptr;
+    const bool quick = fr.dist_cmin != nullptr && !keep_all;
     if (quick && threadIdx.x == 0) nvr_cull_quick_setup(fr.dist, fr.R, fr.Th, cq);
     __syncthreads();
     for (long long sbase = (long long)blockIdx.x * CULL_SPAN; sbase < n_map; sbase += (long long)gridDim.x * CULL_SPAN) {
@@ -409,7 +410,8 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
                 if (!culled) {                                    // the reference's arithmetic, bit for bit
                     nvr_world_to_pose(fr.R, fr.Th, w, p);
                     nvr_volume_coords(fr.dist, p, c);
-                    if (!(quick && nvr_cull_early_out(fr.dist, fr.dist_cmin, c, thresh))) {
+                    if (keep_all) keep = true;
+                    else if (!(quick && nvr_cull_early_out(fr.dist, fr.dist_cmin, c, thresh))) {
                         float pn;
                         nvr_sample_volume_at(fr.dist, c, 0, 1, &pn);
                         keep = pn < thresh;                       // inb_part_network_multiassign.py:136
@@ -447,7 +449,9 @@ struct __align__(16) KnnRec {      // a flagged (sample, part) pair before the w
     int _pad[3];
 };
 
-template <int MINB>
+// DENSE (NVR_TUNE_DENSE_A1, measurement variant): every survivor is flagged in exactly ONE part -- the one with the smallest
+// weighted neighbour distance (first on ties) -- instead of every part with pdist < thresh; no far-field sharing.
+template <int MINB, bool DENSE = false>
 __global__ void __launch_bounds__(256, MINB)
 k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict__ surv,
       KnnRec* __restrict__ recs, int cap, float4* __restrict__ raws, float* __restrict__ dbg, int far_slot) {
@@ -486,6 +490,38 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
                 qhi[a] = fmaxf(qhi[a], __shfl_xor_sync(0xffffffffu, qhi[a], dd));
             }
         }
+        if constexpr (DENSE) {
+            float best_d = INFINITY;
+            int best_part = 0;
+            KnnRec best;
+#pragma unroll
+            for (int i = 0; i < NVR_KNN; ++i) { best.w[i] = 0.0f; best.idx[i] = 0; }
+#pragma unroll 1
+            for (int part = 0; part < NVR_PARTS; ++part) {
+                Knn4 k;
+                nvr_knn_init(k);
+                knn_part_group(fr, part, p, live, qlo, qhi, k, false, thresh);
+                float w[NVR_KNN];
+                const float pdist = nvr_knn_weights(k, w);
+                if (live) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && pdist < best_d) {
+                    best_d = pdist; best_part = part;
+#pragma unroll
+                    for (int i = 0; i < NVR_KNN; ++i) { best.w[i] = w[i]; best.idx[i] = nvr_knn_idx(k, i); }
+                }
+            }
+            best.surv = s; best._pad[0] = best._pad[1] = best._pad[2] = 0;
+#pragma unroll 1
+            for (int part = 0; part < NVR_PARTS; ++part) {
+                const bool flag = live && best_part == part;
+                const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+                if (!ballot) continue;
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&counters[NVR_CTR_PAIR + part], __popc(ballot));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (flag) recs[(long long)part * cap + wbase + __popc(ballot & ((1u << lane) - 1u))] = best;
+            }
+        } else {
 #pragma unroll 1
         for (int part = 0; part < NVR_PARTS; ++part) {
             Knn4 k;
@@ -525,6 +561,7 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
                     recs[(long long)part * cap + wbase + __popc(ballot & ((1u << lane) - 1u))] = rec;
                 }
             }
+        }
         }
     }
 }
@@ -633,9 +670,37 @@ __device__ __forceinline__ void axis_coord(float u, float size, int res, int& i0
     o = f - (float)i0;
 }
 
+// The 8 corner rows of level l (x = bit 2, y = bit 1, z = bit 0 of the corner index) from the clamped corner coordinates;
+// returns the table the rows index (dense or hash).  Shared by k_embed, k_embed_presum and k_embed_footprint.
+__device__ __forceinline__ const float* level_rows(const GridDev& g, int l, int res, const int i0[3], const int i1[3],
+                                                   bool fast_mod, unsigned int T32, unsigned int row[8]) {
+    if (l < g.start_hash) {                                       // dense level  (:124-129)
+        const unsigned int off = (unsigned int)g.dense_off[l];
+        const unsigned int ax[2] = {(unsigned int)(i0[0] * res * res) + off, (unsigned int)(i1[0] * res * res) + off};
+        const unsigned int ay[2] = {(unsigned int)(i0[1] * res), (unsigned int)(i1[1] * res)};
+        const unsigned int az[2] = {(unsigned int)i0[2], (unsigned int)i1[2]};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) row[c] = ax[(c >> 2) & 1] + ay[(c >> 1) & 1] + az[c & 1];
+        return g.dense;
+    }
+    // hashed level (:132-136), int64 products
+    const unsigned int off = (unsigned int)(l - g.start_hash) * T32;
+    const unsigned long long hx[2] = {(unsigned long long)i0[0], (unsigned long long)i1[0]};
+    const unsigned long long hy[2] = {(unsigned long long)i0[1] * 19349663ull, (unsigned long long)i1[1] * 19349663ull};
+    const unsigned long long hz[2] = {(unsigned long long)i0[2] * 83492791ull, (unsigned long long)i1[2] * 83492791ull};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const unsigned long long h = hx[(c >> 2) & 1] ^ hy[(c >> 1) & 1] ^ hz[c & 1];
+        row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
+    }
+    return g.hash;
+}
+
 __global__ void __launch_bounds__(256, 2)
 k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
-        float* __restrict__ eb, int emb_stride) {
+        float* __restrict__ eb, int emb_stride, int l_begin, int l_end) {
+    // levels [l_begin, l_end) only (the normalised coordinates are written by the launch with l_begin == 0): a part whose
+    // tables exceed the L2 is gathered LEVEL-MAJOR, one launch per L2-sized slice of its tables (nvr_cabi.cu, embed_plan)
     const int n = count_dev ? *count_dev : n_imm;
     const int lane = threadIdx.x & 31, half = lane & 1;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -649,38 +714,17 @@ k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restr
         float u[3];
         nvr_normalise(g, x, u);
         float* o = eb + (long long)pt * emb_stride;
-        if (live && half == 0) { o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; }
+        if (live && half == 0 && l_begin == 0) { o[0] = u[0]; o[1] = u[1]; o[2] = u[2]; }
 #pragma unroll 1
-        for (int l = 0; l < g.n_levels; ++l) {
+        for (int l = l_begin; l < l_end; ++l) {
             const int res = g.res[l];
             const float size = g.size[l];
             int i0[3], i1[3];
             float of[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) axis_coord(u[a], size, res, i0[a], i1[a], of[a]);
-            // per-axis contributions to the row index, then 8 corner rows (x = bit 2, y = bit 1, z = bit 0)
             unsigned int row[8];
-            const float* tab;
-            if (l < g.start_hash) {                               // dense level  (:124-129)
-                tab = g.dense;
-                const unsigned int off = (unsigned int)g.dense_off[l];
-                const unsigned int ax[2] = {(unsigned int)(i0[0] * res * res) + off, (unsigned int)(i1[0] * res * res) + off};
-                const unsigned int ay[2] = {(unsigned int)(i0[1] * res), (unsigned int)(i1[1] * res)};
-                const unsigned int az[2] = {(unsigned int)i0[2], (unsigned int)i1[2]};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) row[c] = ax[(c >> 2) & 1] + ay[(c >> 1) & 1] + az[c & 1];
-            } else {                                              // hashed level (:132-136), int64 products
-                tab = g.hash;
-                const unsigned int off = (unsigned int)(l - g.start_hash) * T32;
-                const unsigned long long hx[2] = {(unsigned long long)i0[0], (unsigned long long)i1[0]};
-                const unsigned long long hy[2] = {(unsigned long long)i0[1] * 19349663ull, (unsigned long long)i1[1] * 19349663ull};
-                const unsigned long long hz[2] = {(unsigned long long)i0[2] * 83492791ull, (unsigned long long)i1[2] * 83492791ull};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const unsigned long long h = hx[(c >> 2) & 1] ^ hy[(c >> 1) & 1] ^ hz[c & 1];
-                    row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
-                }
-            }
+            const float* tab = level_rows(g, l, res, i0, i1, fast_mod, T32, row);
             Sector v[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = ld_sector(tab + (unsigned long long)row[c] * 16 + half * 8);
@@ -738,27 +782,7 @@ k_embed_presum(GridDev g, const float* __restrict__ sd, const float* __restrict_
 #pragma unroll
             for (int a = 0; a < 3; ++a) axis_coord(u[a], g.size[l], res, i0[a], i1[a], of[a]);
             unsigned int row[8];
-            const float* tab;
-            if (l < g.start_hash) {
-                tab = sd;
-                const unsigned int off = (unsigned int)g.dense_off[l];
-                const unsigned int ax[2] = {(unsigned int)(i0[0] * res * res) + off, (unsigned int)(i1[0] * res * res) + off};
-                const unsigned int ay[2] = {(unsigned int)(i0[1] * res), (unsigned int)(i1[1] * res)};
-                const unsigned int az[2] = {(unsigned int)i0[2], (unsigned int)i1[2]};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) row[c] = ax[(c >> 2) & 1] + ay[(c >> 1) & 1] + az[c & 1];
-            } else {
-                tab = sh;
-                const unsigned int off = (unsigned int)(l - g.start_hash) * T32;
-                const unsigned long long hx[2] = {(unsigned long long)i0[0], (unsigned long long)i1[0]};
-                const unsigned long long hy[2] = {(unsigned long long)i0[1] * 19349663ull, (unsigned long long)i1[1] * 19349663ull};
-                const unsigned long long hz[2] = {(unsigned long long)i0[2] * 83492791ull, (unsigned long long)i1[2] * 83492791ull};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const unsigned long long h = hx[(c >> 2) & 1] ^ hy[(c >> 1) & 1] ^ hz[c & 1];
-                    row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
-                }
-            }
+            const float* tab = level_rows(g, l, res, i0, i1, fast_mod, T32, row) == g.dense ? sd : sh;
             float v[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + row[c]);
@@ -769,6 +793,55 @@ k_embed_presum(GridDev g, const float* __restrict__ sd, const float* __restrict_
             o[3 + l] = lev;
         }
     }
+}
+
+// -----------------------------------------------------------------------------------------
+// gather footprint (measurement aid, nvr_gather_footprint): the DISTINCT 32-byte sectors one part's pair list touches.
+// Same walk and index arithmetic as k_embed (lane = 2 * point + half, one sector per lane and corner); instead of
+// loading the sector the lane sets its bit in a bitmap over [dense sectors | hash sectors].
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_embed_footprint(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev,
+                  unsigned int* __restrict__ bitmap, unsigned long long dense_sectors) {
+    const int n = *count_dev;
+    const int lane = threadIdx.x & 31, half = lane & 1;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool fast_mod = g.T_magic40 != 0;
+    const unsigned int T32 = (unsigned int)g.T;
+    for (int base = warp * 16; base < n; base += n_warps * 16) {
+        const int pt = base + (lane >> 1);
+        if (pt >= n) continue;
+        const float* xp = xb + (long long)pt * xstride;
+        const float x[3] = {xp[0], xp[1], xp[2]};
+        float u[3];
+        nvr_normalise(g, x, u);
+#pragma unroll 1
+        for (int l = 0; l < g.n_levels; ++l) {
+            const int res = g.res[l];
+            int i0[3], i1[3];
+            float of[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) axis_coord(u[a], g.size[l], res, i0[a], i1[a], of[a]);
+            unsigned int row[8];
+            const bool dense = level_rows(g, l, res, i0, i1, fast_mod, T32, row) == g.dense;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const unsigned long long sec = (dense ? 0ull : dense_sectors) + (unsigned long long)row[c] * 2 + half;
+                const unsigned int bit = 1u << (sec & 31);
+                unsigned int* w = bitmap + (sec >> 5);
+                if (!(*(volatile unsigned int*)w & bit)) atomicOr(w, bit);
+            }
+        }
+    }
+}
+
+__global__ void k_popcount_words(const unsigned int* __restrict__ words, long long n_words, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (long long)gridDim.x * blockDim.x)
+        acc += __popc(words[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 // -----------------------------------------------------------------------------------------

@@ -19,8 +19,8 @@ _FRAME_KEYS = ("R", "Th", "pbw", "pbounds", "part_pts", "part_pbw", "lengths2", 
                "frame_dim", "latent_index")
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
@@ -126,7 +126,7 @@ class Engine:
             return
         key = tuple((t.data_ptr(), t._version) for t in self._net_tables)
         if key != self._tables_key:
-            self._check(self.lib.nvr_prepare_inference(self._h, 1, _stream_ptr()), "nvr_prepare_inference")
+            self._check(self.lib.nvr_prepare_inference(self._h, 1, _stream_ptr(self.device)), "nvr_prepare_inference")
             self._tables_key = key
 
     def bind_params(self, net) -> None:
@@ -187,10 +187,11 @@ class Engine:
         # same subject / same part split => the KD vertex partition of the previous frame is reused
         lkey = (t["lengths2"].data_ptr(), t["lengths2"]._version)
         if lkey != self._topo_src:
-            self._topo_src = lkey
+            self._topo_src, self._topo_keep = lkey, t["lengths2"]
             self._topo_key = (hash((int(F.maxlen),) + tuple(int(v) for v in t["lengths2"][0].tolist())) & 0x7FFFFFFFFFFFFFFF) | 1
         F.topology_key = self._topo_key
-        self._check(self.lib.nvr_bind_frame(self._h, C.byref(F), _stream_ptr()), "nvr_bind_frame")
+        self._check(self.lib.nvr_bind_frame(self._h, C.byref(F), _stream_ptr(self.device)), "nvr_bind_frame")
+        keep["_src"] = src          # the key holds the SOURCE tensors' addresses: keep them alive so no new tensor can reuse one
         self._frame_key, self._frame_keep = key, keep
 
     # ---- scratch --------------------------------------------------------------------------------
@@ -213,7 +214,7 @@ class Engine:
         occ = torch.empty(n, 1, dtype=torch.float32, device=self.device)
         ws, ws_bytes = self._workspace(n)
         self._check(self.lib.nvr_query_points(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, raw.data_ptr(),
-                                              occ.data_ptr(), ws, ws_bytes, _stream_ptr()), "nvr_query_points")
+                                              occ.data_ptr(), ws, ws_bytes, _stream_ptr(self.device)), "nvr_query_points")
         return raw, occ
 
     def render_rays(self, ray_o, ray_d, near, far, n_samples: int, batch: Optional[Dict] = None, want_raw: bool = False):
@@ -230,7 +231,7 @@ class Engine:
         ws, ws_bytes = self._workspace(R * n_samples)
         self._check(self.lib.nvr_render_rays(self._h, ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(), far.data_ptr(),
                                              R, int(n_samples), rgb.data_ptr(), acc.data_ptr(),
-                                             raw.data_ptr() if want_raw else None, ws, ws_bytes, _stream_ptr()),
+                                             raw.data_ptr() if want_raw else None, ws, ws_bytes, _stream_ptr(self.device)),
                     "nvr_render_rays")
         return (rgb, acc, raw) if want_raw else (rgb, acc)
 
@@ -246,20 +247,20 @@ class Engine:
         ws, ws_bytes = self._workspace(R * n_samples)
         self._check(self.lib.nvr_render_rays_host(self._h, ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(),
                                                   far.data_ptr(), R, int(n_samples), rgb_out.data_ptr(), acc_out.data_ptr(),
-                                                  self._io.data_ptr(), ws, ws_bytes, _stream_ptr()), "nvr_render_rays_host")
+                                                  self._io.data_ptr(), ws, ws_bytes, _stream_ptr(self.device)), "nvr_render_rays_host")
 
     def deformer_residual(self, tpts: torch.Tensor, batch: Dict) -> torch.Tensor:
         self.bind_frame(batch)
         tpts = _dev_f32(tpts, self.device)
         out = torch.empty_like(tpts)
-        self._check(self.lib.nvr_deformer_residual(self._h, tpts.data_ptr(), tpts.shape[0], out.data_ptr(), _stream_ptr()),
+        self._check(self.lib.nvr_deformer_residual(self._h, tpts.data_ptr(), tpts.shape[0], out.data_ptr(), _stream_ptr(self.device)),
                     "nvr_deformer_residual")
         return out
 
     def embed_part(self, part: int, xyz: torch.Tensor) -> torch.Tensor:
         xyz = _dev_f32(xyz, self.device)
         out = torch.empty(xyz.shape[0], 19, dtype=torch.float32, device=self.device)
-        self._check(self.lib.nvr_embed_part(self._h, int(part), xyz.data_ptr(), xyz.shape[0], out.data_ptr(), _stream_ptr()),
+        self._check(self.lib.nvr_embed_part(self._h, int(part), xyz.data_ptr(), xyz.shape[0], out.data_ptr(), _stream_ptr(self.device)),
                     "nvr_embed_part")
         return out
 
@@ -273,7 +274,7 @@ class Engine:
         raw = torch.empty(n, 4, dtype=torch.float32, device=self.device)
         ws, ws_bytes = self._workspace(n)
         self._check(self.lib.nvr_part_mlp(self._h, int(part), e20.data_ptr(), dirs.data_ptr(), n, raw.data_ptr(), ws, ws_bytes,
-                                          _stream_ptr()), "nvr_part_mlp")
+                                          _stream_ptr(self.device)), "nvr_part_mlp")
         return raw
 
     # ---- training ---------------------------------------------------------------------------------
@@ -292,7 +293,7 @@ class Engine:
         self._check(self.lib.nvr_train_forward(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, st["raw"].data_ptr(),
                                                st["occ"].data_ptr(), st["x0"].data_ptr(), st["resd"].data_ptr(),
                                                st["tocc"].data_ptr(), st["sample_of_slot"].data_ptr(), st["ws"].data_ptr(),
-                                               st["ws"].numel(), _stream_ptr()), "nvr_train_forward")
+                                               st["ws"].numel(), _stream_ptr(self.device)), "nvr_train_forward")
         st["n_surv"] = int(self.counters()["n_survivors"]) if n else 0      # one host sync (the reference has seven)
         return st
 
@@ -302,13 +303,13 @@ class Engine:
         n = st["n"]
         scratch = torch.empty(int(self.lib.nvr_train_scratch_bytes(self._h, max(n, 64))), dtype=torch.uint8, device=self.device)
         G = _params_struct(net, grads)
-        ptr = lambda t: 0 if t is None else _dev_f32(t, self.device).data_ptr()
         d_raw = _dev_f32(d_raw, self.device)
-        keep = [_dev_f32(t, self.device) for t in (d_resd, d_tocc) if t is not None]
+        d_resd = None if d_resd is None else _dev_f32(d_resd, self.device)      # converted ONCE: the pointers below are theirs
+        d_tocc = None if d_tocc is None else _dev_f32(d_tocc, self.device)
+        ptr = lambda t: 0 if t is None else t.data_ptr()
         self._check(self.lib.nvr_train_backward(self._h, d_raw.data_ptr(), ptr(d_resd), ptr(d_tocc), st["x0"].data_ptr(), n,
                                                 C.byref(G), st["ws"].data_ptr(), st["ws"].numel(), scratch.data_ptr(),
-                                                scratch.numel(), _stream_ptr()), "nvr_train_backward")
-        del keep
+                                                scratch.numel(), _stream_ptr(self.device)), "nvr_train_backward")
 
     def deformer_backward(self, tpts: torch.Tensor, d_resd: torch.Tensor, batch: Dict, net, grads: Dict[str, torch.Tensor]) -> None:
         self.bind_params(net)
@@ -316,7 +317,7 @@ class Engine:
         tpts, d_resd = _dev_f32(tpts.reshape(-1, 3), self.device), _dev_f32(d_resd.reshape(-1, 3), self.device)
         G = _params_struct(net, grads)
         self._check(self.lib.nvr_deformer_backward(self._h, tpts.data_ptr(), d_resd.data_ptr(), tpts.shape[0], C.byref(G),
-                                                   _stream_ptr()), "nvr_deformer_backward")
+                                                   _stream_ptr(self.device)), "nvr_deformer_backward")
 
     def composite_forward(self, raw: torch.Tensor):
         raw = _dev_f32(raw, self.device)
@@ -325,7 +326,7 @@ class Engine:
         rgb = torch.empty(R, 3, dtype=torch.float32, device=self.device)
         acc = torch.empty(R, dtype=torch.float32, device=self.device)
         self._check(self.lib.nvr_composite_forward(self._h, raw.data_ptr(), R, S, w.data_ptr(), rgb.data_ptr(), acc.data_ptr(),
-                                                   _stream_ptr()), "nvr_composite_forward")
+                                                   _stream_ptr(self.device)), "nvr_composite_forward")
         return w, rgb, acc
 
     def composite_backward(self, raw: torch.Tensor, d_w, d_rgb, d_acc) -> torch.Tensor:
@@ -334,7 +335,7 @@ class Engine:
         d_raw = torch.empty(R, S, 4, dtype=torch.float32, device=self.device)
         ts = [None if t is None else _dev_f32(t, self.device) for t in (d_w, d_rgb, d_acc)]
         self._check(self.lib.nvr_composite_backward(self._h, raw.data_ptr(), R, S, *[0 if t is None else t.data_ptr() for t in ts],
-                                                    d_raw.data_ptr(), _stream_ptr()), "nvr_composite_backward")
+                                                    d_raw.data_ptr(), _stream_ptr(self.device)), "nvr_composite_backward")
         return d_raw
 
     def query_points_debug(self, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict):
@@ -349,7 +350,7 @@ class Engine:
         ws, ws_bytes = self._workspace(n)
         self.max_points_per_pass = keep
         self._check(self.lib.nvr_query_points_debug(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, raw.data_ptr(),
-                                                    surv.data_ptr(), warp.data_ptr(), ws, ws_bytes, _stream_ptr()),
+                                                    surv.data_ptr(), warp.data_ptr(), ws, ws_bytes, _stream_ptr(self.device)),
                     "nvr_query_points_debug")
         return raw, surv, warp
 
@@ -360,10 +361,20 @@ class Engine:
         p = cabi.NvrStageProfile()
         self._check(self.lib.nvr_profile_read(self._h, C.byref(p)), "nvr_profile_read")
         return {"ms": dict(zip(cabi.STAGE_NAMES, list(p.ms))), "launches": dict(zip(cabi.STAGE_NAMES, list(p.launches))),
-                "passes": p.passes, "survivors": p.survivors, "pairs": list(p.pairs), "far_pairs": list(p.far_pairs)}
+                "passes": p.passes, "survivors": p.survivors, "pairs": list(p.pairs), "far_pairs": list(p.far_pairs),
+                "embed_part_ms": list(p.embed_part_ms), "mlp_part_ms": list(p.mlp_part_ms)}
+
+    def gather_footprint(self):
+        """Distinct 32-byte table sectors the last (single-pass) render's pair lists touch, per part (measurement aid)."""
+        out = (C.c_int64 * NUM_PARTS)()
+        if self._ws is None:
+            raise RuntimeError("gather_footprint: render something first")
+        self._check(self.lib.nvr_gather_footprint(self._h, self._ws.data_ptr(), self._ws.numel(), out, _stream_ptr(self.device)),
+                    "nvr_gather_footprint")
+        return list(out)
 
     def counters(self) -> Dict[str, int]:
         c = cabi.NvrCounters()
-        self._check(self.lib.nvr_read_counters(self._h, C.byref(c), _stream_ptr()), "nvr_read_counters")
+        self._check(self.lib.nvr_read_counters(self._h, C.byref(c), _stream_ptr(self.device)), "nvr_read_counters")
         return {"n_points": c.n_points, "n_survivors": c.n_survivors, "n_pairs": list(c.n_pairs),
                 "n_far_pairs": list(c.n_far_pairs), "kernel_launches": c.kernel_launches}

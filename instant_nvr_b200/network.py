@@ -45,8 +45,11 @@ class Network(nn.Module):
         """The CUDA engine bound to this module's parameter storages (created lazily, re-bound
         when parameters moved / were replaced, e.g. after load_state_dict or .cuda())."""
         from .engine import Engine
+        dev = next(self.parameters()).device
+        if self._engine is not None and self._engine.device != dev and dev.type == "cuda":
+            self._engine = None                      # the module moved to another GPU: a new handle on that device
         if self._engine is None:
-            self._engine = Engine(self.cfg)
+            self._engine = Engine(self.cfg, device=dev if dev.type == "cuda" else None)
         self._engine.bind_params(self)
         return self._engine
 

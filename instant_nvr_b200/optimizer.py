@@ -64,6 +64,7 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         by_hyper: Dict[tuple, List[cabi.NvrAdamTensor]] = {}
+        touched: List[torch.Tensor] = []
         device = None
         for group in self.param_groups:
             if group.get("amsgrad") or group.get("maximize") or group.get("decoupled_weight_decay"):
@@ -90,6 +91,7 @@ class FusedAdam(torch.optim.Optimizer):
                 t = cabi.NvrAdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                        p.numel(), int(st["step"].item()), float(group["lr"]), float(group["weight_decay"]))
                 by_hyper.setdefault((float(beta1), float(beta2), float(group["eps"])), []).append(t)
+                touched += [p, st["exp_avg"], st["exp_avg_sq"]] + ([g] if self.zero_grad_in_step else [])
         if device is None:
             return loss
         lib, h = aux_handle(device)
@@ -99,6 +101,9 @@ class FusedAdam(torch.optim.Optimizer):
                 arr = (cabi.NvrAdamTensor * len(ts))(*ts)
                 check(lib, h, lib.nvr_adam_step(h, arr, len(ts), beta1, beta2, eps, int(self.zero_grad_in_step), stream),
                       "nvr_adam_step")
+        # the library wrote through raw pointers: tell autograd / anything keyed on tensor versions (the engine's
+        # pre-summed inference tables) that these tensors changed in place, as torch.optim.Adam's in-place ops would
+        torch.autograd.graph.increment_version(touched)
         return loss
 
 

@@ -236,13 +236,15 @@ def make_frame(seed: int = 0, n_verts: int = 6890, pose_scale: float = 0.2, voxe
 
 
 def make_rays(frame: Dict[str, torch.Tensor], H: int, W: int, cam_dist: float = 3.0,
-              tile: Tuple[int, int, int, int] | None = None, azimuth_deg: float = 0.0) -> Dict[str, torch.Tensor]:
+              tile: Tuple[int, int, int, int] | None = None, azimuth_deg: float = 0.0,
+              drop_missing: bool = False) -> Dict[str, torch.Tensor]:
     """Pinhole rays, one per pixel of an H x W image whose frustum just covers the world bbox.
     ``tile=(r0, r1, c0, c1)`` keeps only that pixel window (bounded CPU-baseline samples).
     ``azimuth_deg`` orbits the camera around the vertical axis (multi-view batches).
     Returns ray_o, ray_d (1,R,3), near, far, occupancy (1,R); rays that miss the bbox get a
-    degenerate near == far interval at the bbox centre depth (the reference would drop them
-    via mask_at_box; keeping them fixes R = H*W for the benchmark)."""
+    degenerate near == far interval at the bbox centre depth, or -- ``drop_missing`` -- are dropped as the
+    reference's ``mask_at_box`` does (if_nerf_data_utils.py:92-107, 329-343: only rays with near < far are
+    rendered); ``coord`` (1,R) then holds the row-major pixel index of every kept ray."""
     wb = frame["wbounds"][0].double().numpy()
     centre = wb.mean(0)
     half = (wb[1] - wb[0]) / 2
@@ -272,6 +274,11 @@ def make_rays(frame: Dict[str, torch.Tensor], H: int, W: int, cam_dist: float = 
     near = np.where(hit, tmin, mid)
     far = np.where(hit, tmax, mid)
     f32 = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))[None]
+    if drop_missing:
+        keep = np.nonzero(hit)[0]
+        return {"ray_o": f32(o[keep]), "ray_d": f32(d[keep]), "near": f32(near[keep]), "far": f32(far[keep]),
+                "occupancy": f32(np.ones(len(keep))), "mask_at_box": torch.from_numpy(hit)[None],
+                "coord": torch.from_numpy(keep.astype(np.int64))[None]}
     return {"ray_o": f32(o), "ray_d": f32(d), "near": f32(near), "far": f32(far),
             "occupancy": f32(hit.astype(np.float32)), "mask_at_box": torch.from_numpy(hit)[None]}
 

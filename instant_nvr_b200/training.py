@@ -176,5 +176,8 @@ def render_train(renderer, batch: Dict, epoch: int = -1) -> Dict[str, torch.Tens
     ret.update({"rgb_map": rgb_map[None], "acc_map": acc_map[None], "raw": raw.reshape(1, -1, 4)})
     ret["resd"] = ret["resd"].reshape(n_batch, ret["tpts"].shape[1], 3)                         # :134-136: (1, 5N', 3) out of the renderer
     if cfg.use_freespace_loss:                                                                  # :118-121
-        ret["freespace_occupancy"] = raw[..., 3][batch["occupancy"][0] == 0][None]
+        # the reference's local `occ` is, by then, the PREDICTED occupancy raw[..., 3] (it overwrites the argument, :71), so
+        # the selection is "samples whose predicted occupancy is exactly 0" and the result is (1, K)
+        occ_pred = raw[..., 3]
+        ret["freespace_occupancy"] = occ_pred[occ_pred == 0][None]
     return ret

@@ -223,6 +223,28 @@ def grid_embed(sd, prefix: str, xyz, sum_features: bool):
     return torch.cat([u, val], dim=-1)                                      # :173
 
 
+def grid_rows(sd, prefix: str, xyz):
+    """The table rows grid_embed reads for xyz (N,3): (N, L, 8) int64, dense rows numbered [0, D) and the rows of hashed level
+    l as D + (l - start_hash) * T + idx (D = total dense rows).  Same index arithmetic as grid_embed (:112-136); used by the
+    tests of the gather-footprint measurement aid."""
+    res, T, sh = grid_geometry(sd, prefix)
+    bounds, size, esum, offs = sd[prefix + "bounds"], sd[prefix + "entries_size"], sd[prefix + "entries_sum"], sd[prefix + "offsets"]
+    D = int(sd[prefix + "dense"].shape[0])
+    u = (xyz - bounds[0]) / (bounds[1] - bounds[0])
+    rows = []
+    for l in range(len(res)):
+        f = u / size[l]
+        i = (f[:, None] + offs[None]).long().clip(0, res[l] - 1)
+        if l < sh:
+            idx = i[..., 0] * (res[l] ** 2) + i[..., 1] * res[l] + i[..., 2]
+            if l > 0:
+                idx = idx + int(esum[l - 1])
+        else:
+            idx = (i[..., 0] * PRIMES[0] ^ i[..., 1] * PRIMES[1] ^ i[..., 2] * PRIMES[2]) % T + D + (l - sh) * T
+        rows.append(idx)
+    return torch.stack(rows, 1)
+
+
 # --------------------------------------------------------------------------------------
 # MLPs, view-direction encoding, deformer, part network
 # --------------------------------------------------------------------------------------

@@ -480,6 +480,103 @@ def test_full_size_properties_c4_c5(full):
     assert (acc_p.double() - (1 - torch.prod(1 - alpha, dim=-1))).abs().max() < 1e-5
 
 
+@pytest.fixture(scope="module")
+def full_gain1(full):
+    """The same shipped-size network with the reference's OWN init magnitudes (table gain 1): the strict 1e-4 bound applies to
+    every sample."""
+    from instant_nvr_b200.network import Network
+    sd1 = {k: (v / 50.0 if k.endswith((".embedder.dense", ".embedder.hash")) and "part_networks" in k else v.clone())
+           for k, v in full["sd"].items()}
+    gnet = Network(full["cfg"], device="cpu")
+    gnet.load_state_dict(sd1)
+    return dict(cfg=full["cfg"], frame=full["frame"], sd=sd1, net=gnet.cuda().eval())
+
+
+CONFIG_SHAPES = {"c2": (512, 512, 128), "c4": (1024, 1024, 64), "c5": (2160, 3840, 256)}
+
+
+@pytest.mark.parametrize("name", ["c2", "c4", "c5"])
+@pytest.mark.parametrize("gain", [50.0, 1.0])
+def test_baseline_configs_ray_subset_vs_oracle(full, full_gain1, name, gain):
+    """BASELINE.json configs[1] / [3] / [4] at their FULL sizes and the shipped table sizes: a random 4096-ray subset of the
+    frame's (bbox-hitting) rays, rendered (a) inside the whole-frame render and (b) on its own, against the oracle --
+    per-sample raw, rgb_map, acc_map within 1e-4 (strict for every sample at the reference's init magnitudes, gain 1; at
+    gain 50 samples evaluated outside a part's bbox carry the reference's own extrapolation noise and are counted)."""
+    from instant_nvr_b200.synthetic import make_rays
+    fx = full if gain == 50.0 else full_gain1
+    cfg, frame, sd, net = fx["cfg"], fx["frame"], fx["sd"], fx["net"]
+    H, W, S = CONFIG_SHAPES[name]
+    eng = net.engine()
+    rays = make_rays(frame, H, W, drop_missing=True)
+    gb = to_cuda({**frame, **rays})
+    o, d, n, f = gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0]
+    R = o.shape[0]
+    sel = torch.randperm(R, generator=torch.Generator().manual_seed(7))[:4096].sort().values
+    t0 = time.time()
+    rgb_full, acc_full = eng.render_rays(o, d, n, f, S, batch=gb)                       # the whole frame
+    torch.cuda.synchronize()
+    t_full = time.time() - t0
+    sg = sel.cuda()
+    rgb_s, acc_s, raw_s = eng.render_rays(o[sg], d[sg], n[sg], f[sg], S, want_raw=True)
+    assert torch.equal(rgb_s, rgb_full[sg]) and torch.equal(acc_s, acc_full[sg])       # the subset IS the frame's pixels
+    sub = {**frame, **{k: rays[k][:, sel] for k in ("ray_o", "ray_d", "near", "far")}}
+    b = O.strip_batch(sub)
+    pts, _ = O.sample_along_rays(b["ray_o"], b["ray_d"], b["near"], b["far"], S)
+    vd = b["ray_d"][:, None].expand(-1, S, 3).reshape(-1, 3)
+    t0 = time.time()
+    with torch.no_grad():
+        raw_o, _, st = O.network_forward(sd, pts.reshape(-1, 3), vd, b, cfg.smpl_thresh, want_stages=True)
+        _, rgb_o, acc_o = O.composite(raw_o.reshape(-1, S, 4))
+    t_oracle = time.time() - t0
+    stats = _compare_raw(f"{name}_subset_raw_gain{int(gain)}", raw_s.cpu(), raw_o, st, sd, strict_all=(gain == 1.0))
+    rgb_err = (rgb_s.cpu() - rgb_o).abs().max().item()
+    acc_err = (acc_s.cpu() - acc_o).abs().max().item()
+    psnr = O.psnr(rgb_s.cpu(), rgb_o)
+    diag(f"{name}_subset_maps_gain{int(gain)}", rays=R, subset=int(sel.numel()), samples=int(sel.numel()) * S, rgb_err=rgb_err, acc_err=acc_err,
+         psnr_vs_oracle=psnr, frame_seconds=t_full, oracle_seconds=t_oracle, active=stats["active"])
+    assert stats["active"] > 1000
+    if gain == 1.0:
+        assert rgb_err < 1e-4 and acc_err < 1e-4
+    assert psnr > 60.0
+
+
+def test_dense_a1_variant_is_dense(gpu):
+    """NVR_TUNE_DENSE_A1 (bench.py's `dense_a1` line): every sample survives the cull and is flagged in exactly one
+    part, so evaluated pairs == samples."""
+    from instant_nvr_b200.engine import Engine
+    cfg, gb, net = gpu["cfg"], gpu["gbatch"], gpu["nets"][1.0]
+    eng = Engine(cfg, tune=16)
+    eng.bind_params(net)
+    S = cfg.N_samples
+    rgb, acc, raw = eng.render_rays(gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0], S, want_raw=True, batch=gb)
+    c = eng.counters()
+    n = gb["ray_o"].shape[1] * S
+    assert c["n_survivors"] == n and sum(c["n_pairs"]) == n and sum(c["n_far_pairs"]) == 0
+    assert torch.isfinite(raw).all() and torch.isfinite(rgb).all()
+    uniq = eng.gather_footprint()
+    assert all(u >= 0 for u in uniq) and sum(uniq) > 0
+
+
+def test_gather_footprint_counts_distinct_sectors(gpu):
+    """nvr_gather_footprint against a direct count with the oracle's row arithmetic: distinct (row, half) sectors the flagged
+    pairs of a render touch, per part."""
+    from instant_nvr_b200.engine import Engine
+    cfg, gb, net, sd = gpu["cfg"], gpu["gbatch"], gpu["nets"][200.0], gpu["sds"][200.0]
+    eng = Engine(cfg, tune=8)                                 # every pair on its own: the pair lists are the reference's flagged pairs
+    eng.bind_params(net)
+    wpts, vd, b = _points(gpu)
+    eng.query_points(wpts.cuda(), vd.cuda(), gb)
+    uniq = eng.gather_footprint()
+    _, _, st = O.network_forward(sd, wpts, vd, b, cfg.smpl_thresh, want_stages=True)
+    for pid in range(5):
+        x = st["tpose"][:, pid][st["flag"][:, pid]]
+        pre = f"tpose_human.part_networks.{pid}.embedder."
+        rows = O.grid_rows(sd, pre, x)
+        n_ref = 2 * int(torch.unique(rows).numel())
+        diag("gather_footprint", part=pid, pairs=int(x.shape[0]), unique_sectors=int(uniq[pid]), oracle=n_ref)
+        assert abs(uniq[pid] - n_ref) <= max(4, n_ref // 500), (pid, uniq[pid], n_ref)    # threshold-edge pairs may differ
+
+
 def test_inference_tables_match_full_tables(gpu):
     """Opt-in pre-summed inference tables: same render within fp32 re-association, and they follow in-place updates."""
     from instant_nvr_b200.engine import Engine

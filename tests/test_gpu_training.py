@@ -227,3 +227,139 @@ def test_render_train_outputs_match_oracle(setup):
     assert ret["oresd"].shape == (1, 2 * Kg, 3) and abs(Kg - K) <= 1   # same pairs selected (|tocc - 0.5| < 0.02; a pair whose
     if K and Kg == K:                                                  # tocc sits on the edge to 1e-6 may fall either way) ...
         assert (ret["oresd"][:, :K].cpu() - ref["oresd"][:, :K]).abs().max() < 1e-5     # ... and the same gathered residuals
+
+
+@pytest.fixture(scope="module")
+def setup_full():
+    """BASELINE.json configs[2]: 1024 rays x 64 samples per step with the SHIPPED table sizes (1.14 GB), reference init (gain 1)."""
+    from instant_nvr_b200.config import PathConfig
+    from instant_nvr_b200.network import Network
+    from instant_nvr_b200.synthetic import fill_weights, make_frame, make_rays
+    cfg = PathConfig.inb_377(N_samples=64).with_(use_reg_distortion=True)
+    frame = make_frame(seed=4)
+    net = Network(cfg, device="cpu")
+    fill_weights(net.state_dict(), seed=5, table_gain=1.0, bounds=frame["bounds"][0])
+    sd = net.state_dict()
+    gnet = Network(cfg, device="cpu")
+    gnet.load_state_dict(sd)
+    gnet = gnet.cuda()
+    rays = make_rays(frame, 32, 32)
+    gbatch = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in {**frame, **rays}.items()}
+    return dict(cfg=cfg, frame=frame, rays=rays, sd=sd, net=gnet, gbatch=gbatch)
+
+
+def test_train_config3_full_tables_vs_oracle_autograd(setup_full):
+    """The training step's forward + backward at configs[2] size with the full-size tables against the oracle's autograd:
+    forward outputs within 1e-4 (strict: reference-init magnitudes), every trainable tensor's gradient within 2e-3 of its
+    scale, the big tables included (1M-row hash levels, int64 hash products past 2^32 in the backward's index arithmetic)."""
+    import json
+    s = setup_full
+    cfg, net, sd, frame, rays = s["cfg"], s["net"], s["sd"], s["frame"], s["rays"]
+    b = O.strip_batch({**frame, **rays})
+    pts, _ = O.sample_along_rays(b["ray_o"], b["ray_d"], b["near"], b["far"], cfg.N_samples)
+    wpts = pts.reshape(-1, 3).contiguous()
+    vd = b["ray_d"][:, None].expand(-1, cfg.N_samples, 3).reshape(-1, 3).contiguous()
+    N = wpts.shape[0]
+    assert N == 1024 * 64
+    g = torch.Generator().manual_seed(31)
+    Wr = torch.randn(N, 4, generator=g)
+    names = _trainable_names(net)
+    sdr = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    raw_o, occ_o, st = O.network_forward(sdr, wpts, vd, b, cfg.smpl_thresh, want_stages=True)
+    M = st["pind"].shape[0]
+    Wd = torch.randn(M, 5, 3, generator=g)
+    loss_o = (raw_o * Wr).sum() + 3.0 * (st["resd"] * Wd).sum() + 0.5 * occ_o.sum()
+    loss_o.backward()
+
+    net.train()
+    for p in net.parameters():
+        p.grad = None
+    ret = net(wpts.cuda(), vd.cuda(), None, s["gbatch"])
+    raw_err = (ret["raw"][0].cpu() - raw_o.detach()).abs().max().item()
+    resd_err = (ret["resd"][0].cpu() - st["resd"].detach()).abs().max().item()
+    tocc_err = (ret["tocc"].reshape(M, 5).cpu() - st["raws"][..., 3].detach()).abs().max().item()
+    assert ret["resd"].shape == (1, M, 5, 3)
+    assert raw_err < 1e-4 and tocc_err < 1e-4 and resd_err < 1e-5, (raw_err, tocc_err, resd_err)
+    loss = (ret["raw"][0] * Wr.cuda()).sum() + 3.0 * (ret["resd"][0] * Wd.cuda()).sum() + 0.5 * ret["occ"].sum()
+    loss.backward()
+    net.eval()
+    params = dict(net.named_parameters())
+    worst = {}
+    for n in names:
+        ref = sdr[n].grad if sdr[n].grad is not None else torch.zeros_like(sdr[n])
+        worst[n] = _rel(params[n].grad.cpu(), ref)
+        if ref.abs().max() > 0:
+            assert params[n].grad.abs().max() > 0, n
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:6]
+    print("[train c3] survivors", M, "fwd err raw/tocc/resd", raw_err, tocc_err, resd_err, "worst grads", top)
+    os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(REPO, "gpurun_out", "diag.jsonl"), "a") as f:
+        f.write(json.dumps({"test": "train_config3_full", "survivors": int(M), "raw_err": raw_err, "tocc_err": tocc_err, "resd_err": resd_err,
+                            "worst_grad_rel": top[0][1], "worst_grad_name": top[0][0]}) + "\n")
+    bad = {k: v for k, v in worst.items() if v > 2e-3}
+    assert not bad, bad
+
+
+def test_training_forward_strict_at_reference_init():
+    """Same small config as `setup`, but with the reference's own init magnitudes (table gain 1): raw / tocc within the
+    north-star's 1e-4 (the loose 1e-3 above is extrapolation noise at gain 200)."""
+    from instant_nvr_b200.config import PathConfig
+    from instant_nvr_b200.network import Network
+    from instant_nvr_b200.renderer import Renderer
+    from instant_nvr_b200.synthetic import fill_weights, make_frame, make_rays
+    cfg = PathConfig.inb_377(N_samples=24, log2_T_cap=12).with_(use_reg_distortion=True)
+    frame = make_frame(seed=4)
+    net = Network(cfg, device="cpu")
+    fill_weights(net.state_dict(), seed=4, table_gain=1.0, bounds=frame["bounds"][0])
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    rays = make_rays(frame, 20, 20)
+    gb = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in {**frame, **rays}.items()}
+    ref = O.render_train(sd, {**frame, **rays}, cfg.N_samples, cfg.smpl_thresh, use_pair_reg=True, use_reg_distortion=True)
+    net.train()
+    try:
+        with torch.no_grad():
+            ret = Renderer(net).render(dict(gb))
+    finally:
+        net.eval()
+    assert (ret["raw"].cpu() - ref["raw"]).abs().max() < 1e-4
+    assert (ret["tocc"].cpu() - ref["tocc"]).abs().max() < 1e-4
+    assert (ret["resd"].cpu() - ref["resd"].reshape(1, -1, 3)).abs().max() < 1e-5
+    assert (ret["rgb_map"].cpu() - ref["rgb_map"]).abs().max() < 1e-4 and (ret["acc_map"].cpu() - ref["acc_map"]).abs().max() < 1e-4
+    d, dr = ret["reg_distortion_loss"].cpu(), ref["reg_distortion_loss"]
+    assert (d - dr).abs().max() <= 1e-4 * max(dr.abs().max().item(), 1e-6) + 1e-7
+
+
+def test_fused_adam_step_refreshes_inference_tables():
+    """FusedAdam writes parameters through raw pointers; the engine's pre-summed inference tables are keyed on tensor
+    versions, so the optimizer must bump them -- an eval render after a step must match the full-table render."""
+    from instant_nvr_b200.config import PathConfig
+    from instant_nvr_b200.engine import Engine
+    from instant_nvr_b200.network import Network
+    from instant_nvr_b200.optimizer import FusedAdam
+    from instant_nvr_b200.synthetic import fill_weights, make_frame, make_rays
+    cfg = PathConfig.inb_377(N_samples=16, log2_T_cap=12)
+    frame = make_frame(seed=2)
+    net = Network(cfg, device="cpu")
+    fill_weights(net.state_dict(), seed=2, table_gain=200.0, bounds=frame["bounds"][0])
+    net = net.cuda().eval()
+    rays = make_rays(frame, 16, 16)
+    gb = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in {**frame, **rays}.items()}
+    o, d, n, f = gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0]
+    eng_sum = Engine(cfg, inference_tables=True)
+    eng_sum.bind_params(net)
+    eng_full = Engine(cfg, inference_tables=False)
+    eng_full.bind_params(net)
+    before = eng_sum.render_rays(o, d, n, f, 16, batch=gb)[0].clone()
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = FusedAdam(params, lr=5e-2, eps=1e-15)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for p in params:
+        p.grad = torch.randn(p.shape, device="cuda", generator=gen)
+    v0 = params[0]._version
+    opt.step()
+    assert params[0]._version > v0
+    after_sum = eng_sum.render_rays(o, d, n, f, 16, batch=gb)[0]
+    after_full = eng_full.render_rays(o, d, n, f, 16, batch=gb)[0]
+    assert (after_sum - after_full).abs().max() < 2e-4
+    assert (after_sum - before).abs().max() > 1e-3

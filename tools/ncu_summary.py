@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One line per profiled launch from an ncu report (raw page): the metrics the roofline discussion uses.
-usage: tools/ncu_summary.py <report.ncu-rep> [out.csv]"""
+usage: tools/ncu_summary.py <report.ncu-rep> [out.csv [steps_captured]]"""
 import csv, subprocess, sys, io
 txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
@@ -18,3 +18,10 @@ for r in rows[2:]:
     out.append([r[i].split("(")[0] if h[i] == "Kernel Name" else r[i] for i in idx])
 w = csv.writer(open(sys.argv[2], "w") if len(sys.argv) > 2 else sys.stdout)
 w.writerows(out)
+if len(sys.argv) > 2:
+    # tie the capture to the sources it was taken from (bench.py: roofline.dram.same_sources_as_this_library)
+    import json, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    json.dump({"csrc_hash": bench.csrc_hash(), "steps_captured": int(sys.argv[3]) if len(sys.argv) > 3 else 1, "report": os.path.basename(sys.argv[1])},
+              open(sys.argv[2].replace(".csv", ".meta.json"), "w"))

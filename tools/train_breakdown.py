@@ -10,7 +10,7 @@ from instant_nvr_b200.renderer import Renderer
 from instant_nvr_b200.synthetic import make_rays
 
 cfg = PathConfig.inb_377(N_samples=64).with_(perturb=1.0, use_reg_distortion=True)
-frame, _ = bench.build_views(1)
+frame, _ = bench.build_views(1, 64, 64)
 with torch.device("cuda"):
     net = Network(cfg)
 net = net.cuda()
