@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--impl", choices=["ours", "reference", "reference-gpu"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="strong")
+    ap.add_argument("--assemble", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: frame assembly by peer-memory stores from the compositing kernel + flag barrier (nvr_render_rays_frame) "
+                         "or by the round-1 path (pad + NCCL all_gather + un-permute)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the supplementary training-step measurement")
     ap.add_argument("--no-extras", action="store_true", help="only the main workload (value, e2e, stage times, roofline)")
@@ -373,8 +376,8 @@ def cpu_state_dict(S, seed=0):
 class Workload:
     """One config's rays sharded over the ranks + the two step functions (device-resident and end-to-end)."""
 
-    def __init__(self, eng, gframe, frame_cpu, cfgd, n_views, rank, world, seed=0):
-        from instant_nvr_b200.sharding import shard_indices
+    def __init__(self, eng, gframe, frame_cpu, cfgd, n_views, rank, world, assemble_mode="peer"):
+        from instant_nvr_b200.sharding import PeerFrame, shard_indices
         from instant_nvr_b200.synthetic import make_rays
         self.eng, self.gframe, self.cfgd, self.rank, self.world = eng, gframe, cfgd, rank, world
         H, W = cfgd["H"], cfgd["W"]
@@ -388,11 +391,19 @@ class Workload:
         self.n_local = idx.numel()
         self.rgb_h, self.acc_h = torch.empty(self.n_local, 3).pin_memory(), torch.empty(self.n_local).pin_memory()
         self.samples_per_step = self.n_total * cfgd["S"]
+        self.pf = PeerFrame(eng, self.n_total, rank, world) if world > 1 and assemble_mode == "peer" else None
+
+    def close(self):
+        if self.pf is not None:
+            self.pf.close()
+            self.pf = None
 
     def step_device(self):
         from instant_nvr_b200.sharding import assemble
         eng, dev = self.eng, self.dev
         eng.bind_frame(self.gframe, force=True)      # every step is a new frame: per-frame preparation is inside the timed region
+        if self.pf is not None:                      # the compositing kernel stores into every rank's frame + one flag barrier
+            return self.pf.render(dev["ray_o"], dev["ray_d"], dev["near"], dev["far"], self.cfgd["S"])
         rgb, acc = eng.render_rays(dev["ray_o"], dev["ray_d"], dev["near"], dev["far"], self.cfgd["S"])
         if self.world > 1:
             return assemble(torch.cat([rgb, acc[:, None]], 1), self.n_total, self.rank, self.world)
@@ -407,8 +418,11 @@ class Workload:
         else:
             # every rank: its own tiles in from pinned host memory, the frame assembled on every GPU, its own tiles back out
             d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
-            rgb, acc = eng.render_rays(d["ray_o"], d["ray_d"], d["near"], d["far"], self.cfgd["S"])
-            assemble(torch.cat([rgb, acc[:, None]], 1), self.n_total, self.rank, self.world)
+            if self.pf is not None:
+                _, rgb, acc = self.pf.render(d["ray_o"], d["ray_d"], d["near"], d["far"], self.cfgd["S"], want_local=True)
+            else:
+                rgb, acc = eng.render_rays(d["ray_o"], d["ray_d"], d["near"], d["far"], self.cfgd["S"])
+                assemble(torch.cat([rgb, acc[:, None]], 1), self.n_total, self.rank, self.world)
             self.rgb_h.copy_(rgb, non_blocking=True)
             self.acc_h.copy_(acc, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -477,7 +491,7 @@ def main():
     gframe = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in frame.items()}
     eng = net.engine()
     eng.bind_frame(gframe)
-    wl = Workload(eng, gframe, frame, cfgd, n_views, rank, world)
+    wl = Workload(eng, gframe, frame, cfgd, n_views, rank, world, args.assemble)
 
     def timed(e, fn, steps, warmup, profile=False, mark=False):
         # mark: cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off sees exactly them)
@@ -614,6 +628,7 @@ def main():
                    "(SURVEY.md 8(d)); fractions are of 148 SMs x 128 lanes x 2 FLOP x SM clock"}
 
     extras = {}
+    wl.close()                                       # one peer frame buffer per engine: the supplementary workloads bring their own
     if not args.no_extras:
         # ---- c4 / c5 (BASELINE.json configs[3], [4]) at this N: one frame split over the ranks, a few steps each
         for name in ("c4", "c5"):
@@ -621,7 +636,7 @@ def main():
                 continue
             try:
                 cd = CONFIGS[name]
-                w2 = Workload(eng, gframe, frame, cd, 1, rank, world)
+                w2 = Workload(eng, gframe, frame, cd, 1, rank, world, args.assemble)
                 st = 5 if name == "c4" else 2
                 m, _, _, _ = timed(eng, w2.step_device, st, 1)
                 m2, _, _, _ = timed(eng, w2.step_e2e, st, 1)
@@ -630,6 +645,7 @@ def main():
                                 "rays_per_gpu": w2.n_local, "scaling": "strong",
                                 "e2e": {"value": w2.samples_per_step * st / (m2 * 1e-3), "ms_per_frame": m2 / st,
                                         "h2d_bytes_per_step": w2.n_local * 32 * world, "d2h_bytes_per_step": w2.n_local * 16 * world}}
+                w2.close()
                 del w2
                 torch.cuda.empty_cache()
             except Exception as ex:     # a supplementary line must never cost the headline
@@ -697,7 +713,9 @@ def main():
                        "rays_rendered": wl.n_total, "rays_per_gpu": wl.n_local, "samples_per_ray": S,
                        "rays_note": "rays = the pixels whose ray hits the subject's bounding box (near < far), as the reference's "
                                     "mask_at_box selects them; the remaining pixels are background and are not rendered or counted",
-                       "sharding": "interleaved 1024-ray tiles + 1 all_gather" if world > 1 else "single GPU",
+                       "sharding": ("single GPU" if world == 1 else "interleaved 1024-ray tiles; frame assembled by peer-memory stores from the "
+                                    "compositing kernel + 1 flag barrier (nvr_render_rays_frame)" if args.assemble == "peer" else
+                                    "interleaved 1024-ray tiles + pad + NCCL all_gather + un-permute"),
                        "l2": "no flush: each step streams 1.14 GB of tables + ~GBs of workspace, far above the 126 MB L2",
                        "survivor_fraction": per(prof["survivors"]) / (wl.n_local * S),
                        "active_pairs_per_sample": per(pairs) / (wl.n_local * S),

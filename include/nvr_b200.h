@@ -128,9 +128,9 @@ typedef struct NvrConfig {
                                           and every sample is flagged in exactly ONE part (the part with the smallest weighted
                                           neighbour distance, first on ties), so (sample, part) pairs == samples whatever the input.
                                           Not the reference's semantics; bench.py's `dense_a1` line only */
-#define NVR_TUNE_NO_LEVEL_MAJOR 64u     /* gather every part in ONE launch over all 16 levels.  By default a part whose tables are
-                                          several times the L2 (body: 724 MB) is gathered level-major, one launch per <= 72 MB slice of
-                                          its tables, so each row comes from HBM once instead of ~6x (identical results) */
+#define NVR_TUNE_LEVEL_MAJOR 64u        /* experiment: gather a part whose tables are several times the L2 (body: 724 MB) level-major,
+                                          one launch per <= 72 MB slice of its tables (identical results; 2.4x less DRAM traffic, no
+                                          faster: L2 -> SM row delivery is the same ~6.5 TB/s bound) */
 #define NVR_TUNE_SERIAL 32u            /* one stream, no CUDA graph: every launch of a pass back to back on the caller's stream
                                           (what the per-stage CUDA-event timing of nvr_profile needs; nvr_profile(h, 1) implies it) */
 
@@ -179,6 +179,30 @@ int nvr_render_rays_host(NvrHandle h, const float* ray_o_host, const float* ray_
                          const float* near_host, const float* far_host, int64_t n_rays,
                          int32_t n_samples, float* rgb_map_host, float* acc_map_host, void* dev_io,
                          void* workspace, size_t ws_bytes, void* stream);
+
+/* == Multi-GPU frame assembly over NVLink peer memory (the reference renders on one device,
+ *    run.py / inb_renderer.py:204-239, so there is no reference counterpart) ==
+ * Rays shard over `world` ranks (one process per GPU) in interleaved tiles of `tile` rays: tile t of the frame's n_rays_total
+ * rays belongs to rank t % world, and a rank's shard lists its tiles in ascending order.  nvr_frame_create allocates this
+ * rank's frame buffer (two slots of n_rays_total x [r, g, b, acc] + barrier flags) and returns its CUDA IPC handle; the host
+ * side exchanges the handles over its own control plane (instant_nvr_b200/sharding.py: torch.distributed.all_gather_object)
+ * and passes all `world` of them, in rank order, to nvr_frame_connect (entry `rank` is ignored).  world == 1 needs no handles.
+ * nvr_render_rays_frame == nvr_render_rays on this rank's shard whose compositing kernel ALSO stores every finished ray to its
+ * final position in every rank's frame (NVLink peer stores), followed by one flag barrier: when the work enqueued by the call
+ * has run, *frame_out (device pointer, n_rays_total x 4 floats) holds the complete frame on every rank.  It stays valid until
+ * the call after the next one (the two slots alternate).  rgb_map / acc_map (the shard's own pixels) may both be NULL.
+ * nvr_allgather_frame is the unfused form for pixels that already exist: scatter rgb_map (n,3) / acc_map (n) + barrier.
+ * Every rank must make the same sequence of frame calls (the barrier waits for all of them). */
+typedef struct NvrIpcHandle { unsigned char bytes[64]; } NvrIpcHandle;
+int nvr_frame_create(NvrHandle h, int64_t n_rays_total, int32_t rank, int32_t world, int32_t tile, NvrIpcHandle* handle_out);
+int nvr_frame_connect(NvrHandle h, const NvrIpcHandle* handles);
+int nvr_frame_disconnect(NvrHandle h);   /* unmap the peers' buffers; EVERY rank must have done this before any rank ... */
+int nvr_frame_destroy(NvrHandle h);      /* ... frees its own (the host side puts a barrier between the two) */
+int nvr_render_rays_frame(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                          int64_t n_rays_local, int32_t n_samples, float* rgb_map, float* acc_map,
+                          void* workspace, size_t ws_bytes, void* stream, const float** frame_out);
+int nvr_allgather_frame(NvrHandle h, const float* rgb_map, const float* acc_map, int64_t n_rays_local, void* stream,
+                        const float** frame_out);
 
 /* == Network.resd (inb_part_network_multiassign.py:122-124; uv_deformer.py:23-45, flag=None) ==
  * canonical points (n,3) -> 0.05*tanh(MLP(grid(u,v,t))) (n,3). */

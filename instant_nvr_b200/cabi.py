@@ -73,6 +73,10 @@ class NvrStageProfile(C.Structure):
                 ("embed_part_ms", C.c_double * NUM_PARTS), ("mlp_part_ms", C.c_double * NUM_PARTS)]
 
 
+class NvrIpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
 class NvrAdamTensor(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("numel", C.c_int64), ("step", C.c_int64), ("lr", C.c_double), ("weight_decay", C.c_double)]
@@ -105,6 +109,13 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nvr_render_rays_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nvr_frame_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(NvrIpcHandle)]),
+    "nvr_frame_connect": (C.c_int, [C.c_void_p, C.POINTER(NvrIpcHandle)]),
+    "nvr_frame_disconnect": (C.c_int, [C.c_void_p]),
+    "nvr_frame_destroy": (C.c_int, [C.c_void_p]),
+    "nvr_render_rays_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nvr_allgather_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]),
     "nvr_deformer_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nvr_embed_part": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "nvr_part_mlp": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -44,6 +44,11 @@ struct NvrEngine {
     int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
     long long launches = 0;
     long long last_points = 0;
+    // multi-GPU frame assembly (nvr_frame.cuh): the local buffer [flags | slot 0 | slot 1] and the peers' mappings
+    struct PeerFrame {
+        void* local = nullptr; void* peer[NVR_MAX_RANKS] = {nullptr};
+        long long n_total = 0; int rank = 0, world = 0, tile = 1024; unsigned int epoch = 0; bool connected = false;
+    } pf;
     // optional per-stage timing (nvr_profile): event pairs around every launch + per-pass counter snapshots
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -105,6 +110,8 @@ static GridDev to_dev(const NvrGrid& g) {
 }
 static LinearDev to_dev(const NvrLinear& l) { return LinearDev{l.weight, l.bias, l.in_dim, l.out_dim}; }
 
+static void frame_release(NvrEngine* h);
+
 extern "C" int nvr_abi_version(void) { return NVR_ABI_VERSION; }
 
 extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
@@ -145,6 +152,7 @@ extern "C" int nvr_destroy(NvrHandle h) {
     cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_perm); cudaFree(h->d_part_mlp); cudaFree(h->d_mlp_blocks); cudaFree(h->d_presum); cudaFree(h->d_counters_snapshot);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
+    frame_release(h);
     delete h;
     return 0;
 }
@@ -306,17 +314,17 @@ static int grid_for(long long items, int per_block, int max_blocks) {
     return (int)std::max<long long>(1, std::min<long long>(b, max_blocks));
 }
 
-// Level ranges one part's gather is launched in.  A part whose tables fit the L2 is ONE launch over all levels.  A part
-// whose tables do not (body: 10 hashed levels x 67 MB) would re-read them from HBM several times over -- its pairs arrive
-// in image order, every level's rows are hit at random, and the working set of all levels together is 5x the L2 (ncu r1l:
-// 4.5 GB of DRAM reads for 0.72 GB of tables) -- so it is gathered level-major: consecutive levels are grouped into
-// slices of at most L2_SLICE_BYTES and each slice is one sweep over the pair list, its rows L2-resident for the sweep.
+// Level ranges one part's gather is launched in: ONE launch over all levels, unless NVR_TUNE_LEVEL_MAJOR asks for the
+// level-major experiment -- a part whose tables are several times the L2 (body: 724 MB) gathered in slices of consecutive
+// levels of at most L2_SLICE_BYTES, one sweep over the pair list per slice.  Measured (profiles/r2a): the body part's DRAM
+// reads drop from 4.5 GB to 1.8 GB per frame but its time does not (0.84 against 0.79 ms): a 67 MB hashed level still misses
+// the L2 half of the time, and L2 -> SM delivery of 64-byte rows tops out at the same ~6.5 TB/s as HBM does.  Kept opt-in.
 static const long long L2_SLICE_BYTES = 72ll << 20;
 static const long long L2_SPLIT_ABOVE_BYTES = 384ll << 20;   // ~3x the 126 MB L2 (leg: 290 MB, DRAM traffic already ~1.5x its tables)
 static int embed_plan(const NvrEngine* h, int p, int begin[NVR_MAX_LEVELS], int end[NVR_MAX_LEVELS]) {
     const NvrGrid& g = h->params.part[p].grid;
     const long long total = (dense_rows(g) + hash_rows(g)) * 64;
-    if ((h->cfg.tune & NVR_TUNE_NO_LEVEL_MAJOR) || total <= L2_SPLIT_ABOVE_BYTES) { begin[0] = 0; end[0] = g.n_levels; return 1; }
+    if (!(h->cfg.tune & NVR_TUNE_LEVEL_MAJOR) || total <= L2_SPLIT_ABOVE_BYTES) { begin[0] = 0; end[0] = g.n_levels; return 1; }
     int n = 0, lb = 0;
     long long acc = 0;
     for (int l = 0; l < g.n_levels; ++l) {
@@ -449,12 +457,13 @@ extern "C" int nvr_query_points(NvrHandle h, const float* wpts, const float* vie
     return 0;
 }
 
-extern "C" int nvr_render_rays(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
-                               int64_t n_rays, int32_t n_samples, float* rgb_map, float* acc_map, float* raw,
-                               void* workspace, size_t ws_bytes, void* stream_) {
+static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                            int64_t n_rays, int32_t n_samples, float* rgb_map, float* acc_map, float* raw,
+                            void* workspace, size_t ws_bytes, void* stream_, const FrameOut& fo) {
     if (int rc = ready(h, "nvr_render_rays")) return rc;
     if (n_rays < 0 || n_samples < 1) return fail(h, "nvr_render_rays: bad n_rays / n_samples");
-    if (n_rays > 0 && (!ray_o || !ray_d || !near_ || !far_ || !rgb_map || !acc_map)) return fail(h, "nvr_render_rays: null argument");
+    if (n_rays > 0 && (!ray_o || !ray_d || !near_ || !far_ || ((!rgb_map || !acc_map) && fo.world == 0) || (!rgb_map != !acc_map)))
+        return fail(h, "nvr_render_rays: null argument");
     Workspace w;
     if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_render_rays: workspace too small or not 256-byte aligned");
     const long long rays_per_pass = w.pts / n_samples;
@@ -466,13 +475,137 @@ extern "C" int nvr_render_rays(NvrHandle h, const float* ray_o, const float* ray
         if (int rc = run_pass(h, w, ray_o + r * 3, ray_d + r * 3, near_ + r, far_ + r, m, n_samples, ray_d + r * 3, n_samples, st))
             return rc;
         { StageTimer t(h, st, NVR_STAGE_RESOLVE);
-        k_resolve_rays<<<grid_for(nr, 8, h->sm_count * 8), 256, 0, st>>>(w.surv_of_sample, w.raws, far_raws(h, w, far_collapse(h, nullptr, nullptr)), nr, n_samples, rgb_map + r * 3,
-                                                                       acc_map + r, raw ? (float4*)raw + r * n_samples : nullptr); }
+        k_resolve_rays<<<grid_for(nr, 8, h->sm_count * 8), 256, 0, st>>>(w.surv_of_sample, w.raws, far_raws(h, w, far_collapse(h, nullptr, nullptr)), nr, n_samples,
+                                                                       rgb_map ? rgb_map + r * 3 : nullptr, acc_map ? acc_map + r : nullptr,
+                                                                       raw ? (float4*)raw + r * n_samples : nullptr, fo, r); }
         NVR_CHECK(h, cudaGetLastError());
         h->launches++;
         if (int rc = snapshot_counters(h, w, st)) return rc;
     }
     return 0;
+}
+
+extern "C" int nvr_render_rays(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                               int64_t n_rays, int32_t n_samples, float* rgb_map, float* acc_map, float* raw,
+                               void* workspace, size_t ws_bytes, void* stream_) {
+    FrameOut none;
+    memset(&none, 0, sizeof(none));
+    return render_rays_impl(h, ray_o, ray_d, near_, far_, n_rays, n_samples, rgb_map, acc_map, raw, workspace, ws_bytes, stream_, none);
+}
+
+// ---- multi-GPU frame assembly over peer memory (nvr_frame.cuh) -----------------------------------------------------
+static void frame_release(NvrEngine* h) {
+    NvrEngine::PeerFrame& pf = h->pf;
+    for (int r = 0; r < NVR_MAX_RANKS; ++r)
+        if (pf.peer[r] && pf.peer[r] != pf.local) cudaIpcCloseMemHandle(pf.peer[r]);
+    if (pf.local) cudaFree(pf.local);
+    pf = NvrEngine::PeerFrame();
+}
+
+extern "C" int nvr_frame_create(NvrHandle h, int64_t n_rays_total, int32_t rank, int32_t world, int32_t tile, NvrIpcHandle* handle_out) {
+    if (!h || !handle_out) return fail(h, "nvr_frame_create: null argument");
+    if (world < 1 || world > NVR_MAX_RANKS || rank < 0 || rank >= world || tile < 1 || n_rays_total < 0)
+        return fail(h, "nvr_frame_create: need 1 <= world <= 8, 0 <= rank < world, tile >= 1");
+    if (h->pf.local) return fail(h, "nvr_frame_create: a frame buffer exists (nvr_frame_disconnect on every rank, then nvr_frame_destroy)");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    NvrEngine::PeerFrame& pf = h->pf;
+    const size_t bytes = NVR_FRAME_HEADER_BYTES + 2 * (size_t)std::max<int64_t>(n_rays_total, 1) * sizeof(float4);
+    NVR_CHECK(h, cudaMalloc(&pf.local, bytes));
+    NVR_CHECK(h, cudaMemset(pf.local, 0, bytes));
+    pf.n_total = n_rays_total; pf.rank = rank; pf.world = world; pf.tile = tile; pf.epoch = 0; pf.connected = false;
+    memset(handle_out, 0, sizeof(*handle_out));
+    if (world > 1) {
+        static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(NvrIpcHandle), "NvrIpcHandle holds a cudaIpcMemHandle_t");
+        cudaIpcMemHandle_t ih;
+        NVR_CHECK(h, cudaIpcGetMemHandle(&ih, pf.local));
+        memcpy(handle_out->bytes, &ih, sizeof(ih));
+    }
+    return 0;
+}
+
+extern "C" int nvr_frame_connect(NvrHandle h, const NvrIpcHandle* handles) {
+    if (!h) return 1;
+    NvrEngine::PeerFrame& pf = h->pf;
+    if (!pf.local) return fail(h, "nvr_frame_connect: nvr_frame_create first");
+    if (pf.world > 1 && !handles) return fail(h, "nvr_frame_connect: null argument");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    for (int r = 0; r < pf.world; ++r) {
+        if (r == pf.rank) { pf.peer[r] = pf.local; continue; }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, handles[r].bytes, sizeof(ih));
+        NVR_CHECK(h, cudaIpcOpenMemHandle(&pf.peer[r], ih, cudaIpcMemLazyEnablePeerAccess));
+    }
+    pf.connected = true;
+    return 0;
+}
+
+extern "C" int nvr_frame_disconnect(NvrHandle h) {
+    if (!h) return 0;
+    NvrEngine::PeerFrame& pf = h->pf;
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    NVR_CHECK(h, cudaDeviceSynchronize());
+    for (int r = 0; r < NVR_MAX_RANKS; ++r) {
+        if (pf.peer[r] && pf.peer[r] != pf.local) NVR_CHECK(h, cudaIpcCloseMemHandle(pf.peer[r]));
+        pf.peer[r] = nullptr;
+    }
+    pf.connected = false;
+    return 0;
+}
+
+extern "C" int nvr_frame_destroy(NvrHandle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    frame_release(h);
+    return 0;
+}
+
+// the slot the NEXT frame goes to, as every rank sees it, + the barrier that completes it
+static FrameOut frame_next(NvrEngine* h) {
+    NvrEngine::PeerFrame& pf = h->pf;
+    FrameOut fo;
+    memset(&fo, 0, sizeof(fo));
+    const size_t slot_off = NVR_FRAME_HEADER_BYTES + (size_t)((pf.epoch + 1) & 1) * (size_t)std::max<long long>(pf.n_total, 1) * sizeof(float4);
+    for (int r = 0; r < pf.world; ++r) fo.slot[r] = (float4*)((char*)pf.peer[r] + slot_off);
+    fo.world = pf.world; fo.rank = pf.rank; fo.tile = pf.tile; fo.n_total = pf.n_total;
+    return fo;
+}
+static int frame_finish(NvrEngine* h, const FrameOut& fo, cudaStream_t st, const float** frame_out) {
+    NvrEngine::PeerFrame& pf = h->pf;
+    pf.epoch++;
+    FrameFlags ff;
+    for (int r = 0; r < NVR_MAX_RANKS; ++r) ff.peer[r] = r < pf.world ? (unsigned int*)pf.peer[r] : nullptr;
+    k_frame_barrier<<<1, 32, 0, st>>>(ff, pf.world, pf.rank, pf.epoch);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    if (frame_out) *frame_out = (const float*)fo.slot[pf.rank];
+    return 0;
+}
+
+extern "C" int nvr_render_rays_frame(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                                     int64_t n_rays_local, int32_t n_samples, float* rgb_map, float* acc_map,
+                                     void* workspace, size_t ws_bytes, void* stream_, const float** frame_out) {
+    if (!h) return 1;
+    if (!h->pf.connected) return fail(h, "nvr_render_rays_frame: nvr_frame_create + nvr_frame_connect first");
+    const FrameOut fo = frame_next(h);
+    if (int rc = render_rays_impl(h, ray_o, ray_d, near_, far_, n_rays_local, n_samples, rgb_map, acc_map, nullptr, workspace, ws_bytes, stream_, fo))
+        return rc;
+    return frame_finish(h, fo, (cudaStream_t)stream_, frame_out);
+}
+
+extern "C" int nvr_allgather_frame(NvrHandle h, const float* rgb_map, const float* acc_map, int64_t n_rays_local, void* stream_,
+                                   const float** frame_out) {
+    if (!h) return 1;
+    if (!h->pf.connected) return fail(h, "nvr_allgather_frame: nvr_frame_create + nvr_frame_connect first");
+    if (n_rays_local < 0 || (n_rays_local > 0 && (!rgb_map || !acc_map))) return fail(h, "nvr_allgather_frame: null argument");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    const FrameOut fo = frame_next(h);
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_rays_local > 0) {
+        k_frame_scatter<<<grid_for(n_rays_local, 256, h->sm_count * 4), 256, 0, st>>>(fo, rgb_map, acc_map, n_rays_local);
+        h->launches++;
+    }
+    return frame_finish(h, fo, st, frame_out);
 }
 
 extern "C" int nvr_render_rays_host(NvrHandle h, const float* ray_o_host, const float* ray_d_host, const float* near_host,

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "nvr_math.cuh"
+#include "nvr_frame.cuh"
 
 #define NVR_EMB_STRIDE 20          // 19 used
 #define NVR_CTR_SURV 0
@@ -275,7 +276,8 @@ __device__ __forceinline__ float box_reach2(const float4& lo, const float4& hi, 
 #define KNN_FAR 1
 #define KNN_UNFLAGGED 2
 __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, const float p[3], bool live,
-                                              const float qlo[3], const float qhi[3], Knn4& k, bool allow_skip, float thresh) {
+                                              const float qlo[3], const float qhi[3], Knn4& k, bool allow_skip, float thresh,
+                                              bool allow_unflagged_skip = true) {
     const int lane = threadIdx.x & 31;
     const int c0 = fr.cl_off[part], ncl = fr.cl_off[part + 1] - c0;
     if (ncl <= 0) return KNN_SEARCHED;
@@ -299,7 +301,7 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
     // neighbours are, so sum(w) < NVR_FAR_WSUM for every lane whatever the search would return
     if (allow_skip && best > NVR_FAR_D2 && __reduce_add_sync(0xffffffffu, nv) >= NVR_KNN) return KNN_FAR;
     // U is finite only if some cluster holds >= 4 real vertices, so the four neighbours are real here too
-    if (allow_skip && best > NVR_GAP_FACTOR2 * thresh * thresh && U <= NVR_REACH_D2) return KNN_UNFLAGGED;
+    if (allow_skip && allow_unflagged_skip && best > NVR_GAP_FACTOR2 * thresh * thresh && U <= NVR_REACH_D2) return KNN_UNFLAGGED;
     U *= 1.00001f;
     // the seed first: every live lane's 4th-best is still +inf, so all of them take it
     nvr_knn_scan(fr.verts + (long long)(c0 + seed) * NVR_CL, p, k);
@@ -500,9 +502,11 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
             for (int part = 0; part < NVR_PARTS; ++part) {
                 Knn4 k;
                 nvr_knn_init(k);
-                knn_part_group(fr, part, p, live, qlo, qhi, k, false, thresh);
+                // a part that is far-field for the whole warp (every vertex > 0.73 m away) cannot be the nearest one unless all
+                // five are; it then keeps the zero-weight record of part 0
+                const int group = knn_part_group(fr, part, p, live, qlo, qhi, k, true, thresh, false);
                 float w[NVR_KNN];
-                const float pdist = nvr_knn_weights(k, w);
+                const float pdist = group == KNN_FAR ? INFINITY : nvr_knn_weights(k, w);
                 if (live) raws[(long long)s * NVR_PARTS + part] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (live && pdist < best_d) {
                     best_d = pdist; best_part = part;
@@ -1029,9 +1033,12 @@ __global__ void k_resolve_points(const int* __restrict__ surv_of_sample, const f
 
 // One warp per ray; samples are walked 32 at a time with a shuffle product-scan of (1 - alpha)
 // (net_utils.py:12-15 with epsilon = 0; :39-41).
+// fo.world > 0: the composited ray also goes to its final position in every rank's frame slot (nvr_frame.cuh), lanes 0..world-1
+// storing to one rank each; ray_base = index of this pass's first ray inside the rank's shard.  rgb_map / acc_map may then be null.
 __global__ void __launch_bounds__(256)
 k_resolve_rays(const int* __restrict__ surv_of_sample, const float4* __restrict__ raws, const float4* __restrict__ far_raws,
-               long long n_rays, int S, float* __restrict__ rgb_map, float* __restrict__ acc_map, float4* __restrict__ raw_out) {
+               long long n_rays, int S, float* __restrict__ rgb_map, float* __restrict__ acc_map, float4* __restrict__ raw_out,
+               FrameOut fo, long long ray_base) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -1062,9 +1069,13 @@ k_resolve_rays(const int* __restrict__ surv_of_sample, const float4* __restrict_
             cr += __shfl_xor_sync(0xffffffffu, cr, d); cg += __shfl_xor_sync(0xffffffffu, cg, d);
             cb += __shfl_xor_sync(0xffffffffu, cb, d); ca += __shfl_xor_sync(0xffffffffu, ca, d);
         }
-        if (lane == 0) {
+        if (lane == 0 && rgb_map) {
             rgb_map[ray * 3] = cr; rgb_map[ray * 3 + 1] = cg; rgb_map[ray * 3 + 2] = cb;
             acc_map[ray] = ca;
+        }
+        if (lane < fo.world) {
+            const long long gi = frame_index(fo, ray_base + ray);
+            if (gi < fo.n_total) fo.slot[lane][gi] = make_float4(cr, cg, cb, ca);
         }
     }
 }

@@ -33,6 +33,21 @@ def _worker(rank, world, port, q):
     rgb, acc = render_sharded(fn, o, d, nr, fr, rank, world, tile=256)
     ref_rgb, ref_acc = fn(o, d, nr, fr)
     ok = bool(torch.equal(rgb, ref_rgb) and torch.equal(acc, ref_acc) and ref_acc.max().item() > 0)
+    # the same frame assembled over NVLink peer memory (nvr_render_rays_frame: the compositing kernel stores into every rank's
+    # frame buffer + one flag barrier), three frames in a row (the two slots alternate), then the unfused scatter form
+    from instant_nvr_b200.sharding import PeerFrame, shard_indices
+    n = o.shape[0]
+    idx = shard_indices(n, rank, world, tile=256).cuda()
+    pf = PeerFrame(eng, n, rank, world, tile=256)
+    for it in range(3):
+        frame_t, l_rgb, l_acc = pf.render(o[idx], d[idx], nr[idx], fr[idx], cfg.N_samples, want_local=True)
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(frame_t[:, :3], ref_rgb) and torch.equal(frame_t[:, 3], ref_acc))
+        ok = ok and bool(torch.equal(l_rgb, ref_rgb[idx]) and torch.equal(l_acc, ref_acc[idx]))
+    frame_t = pf.allgather(ref_rgb[idx].contiguous(), ref_acc[idx].contiguous())
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(frame_t[:, :3], ref_rgb) and torch.equal(frame_t[:, 3], ref_acc))
+    pf.close()
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:

@@ -528,11 +528,21 @@ def test_baseline_configs_ray_subset_vs_oracle(full, full_gain1, name, gain):
         raw_o, _, st = O.network_forward(sd, pts.reshape(-1, 3), vd, b, cfg.smpl_thresh, want_stages=True)
         _, rgb_o, acc_o = O.composite(raw_o.reshape(-1, S, 4))
     t_oracle = time.time() - t0
-    stats = _compare_raw(f"{name}_subset_raw_gain{int(gain)}", raw_s.cpu(), raw_o, st, sd, strict_all=(gain == 1.0))
-    rgb_err = (rgb_s.cpu() - rgb_o).abs().max().item()
-    acc_err = (acc_s.cpu() - acc_o).abs().max().item()
-    psnr = O.psnr(rgb_s.cpu(), rgb_o)
-    diag(f"{name}_subset_maps_gain{int(gain)}", rays=R, subset=int(sel.numel()), samples=int(sel.numel()) * S, rgb_err=rgb_err, acc_err=acc_err,
+    # decision flips (module docstring): a sample whose cull distance / a part distance sits within 2e-6 of smpl_thresh may land
+    # on the other side under FMA contraction; such samples (and their rays, for the maps) are excluded and counted
+    edge = (st["pnorm"].reshape(-1) - cfg.smpl_thresh).abs() < 2e-6
+    edge[st["pind"]] |= ((st["pdist"] - cfg.smpl_thresh).abs() < 2e-6).any(-1)
+    n_edge = int(edge.sum())
+    assert n_edge <= 8, n_edge
+    ours_raw, ref_raw = raw_s.cpu().clone(), raw_o.clone()
+    ours_raw[edge] = 0
+    ref_raw[edge] = 0
+    stats = _compare_raw(f"{name}_subset_raw_gain{int(gain)}", ours_raw, ref_raw, st, sd, strict_all=(gain == 1.0))
+    ray_ok = ~edge.reshape(-1, S).any(-1)
+    rgb_err = (rgb_s.cpu() - rgb_o)[ray_ok].abs().max().item()
+    acc_err = (acc_s.cpu() - acc_o)[ray_ok].abs().max().item()
+    psnr = O.psnr(rgb_s.cpu()[ray_ok], rgb_o[ray_ok])
+    diag(f"{name}_subset_maps_gain{int(gain)}", rays=R, subset=int(sel.numel()), samples=int(sel.numel()) * S, threshold_edge_samples=n_edge, rgb_err=rgb_err, acc_err=acc_err,
          psnr_vs_oracle=psnr, frame_seconds=t_full, oracle_seconds=t_oracle, active=stats["active"])
     assert stats["active"] > 1000
     if gain == 1.0:
@@ -575,6 +585,40 @@ def test_gather_footprint_counts_distinct_sectors(gpu):
         n_ref = 2 * int(torch.unique(rows).numel())
         diag("gather_footprint", part=pid, pairs=int(x.shape[0]), unique_sectors=int(uniq[pid]), oracle=n_ref)
         assert abs(uniq[pid] - n_ref) <= max(4, n_ref // 500), (pid, uniq[pid], n_ref)    # threshold-edge pairs may differ
+
+
+def test_peer_frame_single_rank(gpu):
+    """nvr_render_rays_frame at world == 1 (the fused compositing-kernel store + barrier code path on a one-GPU box): the frame is
+    the plain render, for ragged ray counts, several passes and consecutive frames (alternating slots)."""
+    from instant_nvr_b200.sharding import PeerFrame
+    cfg, net, gb = gpu["cfg"], gpu["nets"][200.0], gpu["gbatch"]
+    eng = net.engine()
+    o, d, n, f = gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0]
+    S = cfg.N_samples
+    rgb, acc = eng.render_rays(o, d, n, f, S, batch=gb)
+    R = o.shape[0]
+    pf = PeerFrame(eng, R, 0, 1, tile=64)
+    try:
+        first = pf.render(o, d, n, f, S, batch=gb)
+        a = first.clone()
+        second, l_rgb, l_acc = pf.render(o, d, n, f, S, want_local=True)
+        assert second.data_ptr() != first.data_ptr()
+        for fr in (a, second):
+            assert torch.equal(fr[:, :3], rgb) and torch.equal(fr[:, 3], acc)
+        assert torch.equal(l_rgb, rgb) and torch.equal(l_acc, acc)
+        keep = eng.max_points_per_pass
+        try:
+            eng.max_points_per_pass = 37 * S
+            eng._ws = None
+            third = pf.render(o, d, n, f, S)
+            assert torch.equal(third[:, :3], rgb) and torch.equal(third[:, 3], acc)
+        finally:
+            eng.max_points_per_pass = keep
+            eng._ws = None
+        g = pf.allgather(rgb, acc)
+        assert torch.equal(g[:, :3], rgb) and torch.equal(g[:, 3], acc)
+    finally:
+        pf.close()
 
 
 def test_inference_tables_match_full_tables(gpu):

@@ -22,6 +22,22 @@ def test_shards_partition_the_frame():
     assert max(shares) / min(shares) < 1.2
 
 
+def test_peer_frame_index_formula_matches_shard_indices():
+    """csrc/nvr_frame.cuh frame_index(): local ray i of a rank's shard -> ((i / tile) * world + rank) * tile + i % tile must be
+    exactly the i-th entry of shard_indices (what k_resolve_rays uses to store a ray into the peers' frames)."""
+    for n, world, tile in ((10000, 3, 256), (262144, 8, 1024), (236544, 8, 1024), (5, 2, 4), (1, 4, 16), (1000, 1, 64)):
+        for rank in range(world):
+            idx = shard_indices(n, rank, world, tile)
+            i = torch.arange(idx.numel())
+            gi = ((i // tile) * world + rank) * tile + i % tile
+            assert torch.equal(gi, idx), (n, world, tile, rank)
+            # a shard never holds a local index whose frame index is past the frame except in its last (partial) tile
+            cap = shard_capacity(n, world, tile)
+            j = torch.arange(cap)
+            gj = ((j // tile) * world + rank) * tile + j % tile
+            assert int((gj < n).sum()) == idx.numel()
+
+
 def _fake_render(o, d, near, far):
     # any per-ray function: stands in for the CUDA render (no GPU in the CPU suite)
     rgb = torch.stack([o[:, 0] + near, d[:, 1] * far, o[:, 2] - d[:, 0]], dim=1)

@@ -44,8 +44,12 @@ case "$stage" in
   multi:*)
     n="${stage#multi:}"
     timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -rA --timeout 600 > gpurun_out/pytest_multi.log 2>&1; echo "multi pytest rc=$?"; tail -5 gpurun_out/pytest_multi.log
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 \
-        > gpurun_out/scale_${n}gpu.json 2> gpurun_out/scale_${n}gpu.err; echo "scale $n rc=$?"; cut -c1-1200 gpurun_out/scale_${n}gpu.json; tail -3 gpurun_out/scale_${n}gpu.err ;;
+    for mode in peer nccl; do
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 --assemble $mode \
+          > gpurun_out/scale_${n}gpu_$mode.json 2> gpurun_out/scale_${n}gpu_$mode.err; echo "scale $n $mode rc=$?"
+      python -c "import json; d=json.load(open('gpurun_out/scale_${n}gpu_$mode.json')); print('N=$n $mode', d['value']/1e9, 'G/s', d['ms_per_step'], 'ms; e2e', d['e2e']['value']/1e9, d['e2e']['ms_per_step'], 'c4', d.get('c4',{}).get('value'), d.get('c4',{}).get('ms_per_frame'), 'c5', d.get('c5',{}).get('value'), d.get('c5',{}).get('ms_per_frame'))"
+      tail -3 gpurun_out/scale_${n}gpu_$mode.err
+    done ;;
   *) echo "unknown stage $stage" ;;
 esac
 done
