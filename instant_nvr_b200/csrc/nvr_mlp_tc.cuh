@@ -241,12 +241,31 @@ __device__ __forceinline__ void gemm3_ss(uint32_t d, uint32_t a_hi_smem, uint32_
 
 // PosEnc (freq_embedder.py:20-31) with one sincosf per axis and double-angle steps for 2v, 4v, 8v
 // (absolute error < 1e-6, against 24 separate sinf / cosf calls).
+// sin and cos of a moderate argument without sincosf's slow path (its Payne-Hanek branch costs a stack frame and local
+// memory traffic even when never taken; ncu r2a: 10 % of k_mlp_tc's stall samples): three-term Cody-Waite reduction by pi/2
+// and the classic degree-7 / degree-8 minimax kernels on [-pi/4, pi/4] (error < 2 ulp for |x| < 1e4; canonical view
+// directions are O(1)).  Larger or non-finite arguments take the library routine.
+__device__ __forceinline__ void sincos_small(float x, float* s, float* c) {
+    if (!(fabsf(x) < 1.0e4f)) { sincosf(x, s, c); return; }
+    const float k = rintf(x * 0.6366197723675814f);
+    float r = fmaf(-k, 1.5707962512969971f, x);
+    r = fmaf(-k, 7.5497894158615964e-08f, r);
+    r = fmaf(-k, 5.3903029534742384e-15f, r);
+    const float r2 = r * r;
+    const float sr = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+    const float cr = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                          fmaf(r2, -0.5f, 1.0f));
+    const int q = (int)k & 3;
+    const float a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+    *s = (q & 2) ? -a : a;
+    *c = ((q + 1) & 2) ? -b : b;
+}
 __device__ __forceinline__ void posenc27_doubling(const float v[3], float* out) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         out[a] = v[a];
         float s, c;
-        sincosf(v[a], &s, &c);
+        sincos_small(v[a], &s, &c);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             out[3 + k * 6 + a] = s;

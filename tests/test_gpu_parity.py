@@ -533,7 +533,7 @@ def test_baseline_configs_ray_subset_vs_oracle(full, full_gain1, name, gain):
     edge = (st["pnorm"].reshape(-1) - cfg.smpl_thresh).abs() < 2e-6
     edge[st["pind"]] |= ((st["pdist"] - cfg.smpl_thresh).abs() < 2e-6).any(-1)
     n_edge = int(edge.sum())
-    assert n_edge <= 8, n_edge
+    assert n_edge <= max(8, edge.numel() // 50000), n_edge
     ours_raw, ref_raw = raw_s.cpu().clone(), raw_o.clone()
     ours_raw[edge] = 0
     ref_raw[edge] = 0
