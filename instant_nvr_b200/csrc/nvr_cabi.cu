@@ -241,7 +241,7 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
     k_frame_prep<<<std::min<int>(h->sm_count * 4, (int)((n_vox + 255) / 256)), 256, 0, stream>>>(
         f->pbw, (int)n_vox, f->pbw_channels, h->d_dist);
     float* d_cmin = h->d_dist + n_vox;
-    k_frame_coarse<<<std::min<int>(h->sm_count * 4, (int)((n_coarse + 127) / 128)), 128, 0, stream>>>(
+    k_frame_coarse<<<std::min<int>(h->sm_count * 8, (int)((n_coarse + 3) / 4)), 128, 0, stream>>>(
         h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], d_cmin);
     h->launches++;
     float4* cl_lo = h->d_verts + max_cl * NVR_CL;

@@ -87,11 +87,32 @@ __global__ void k_frame_prep(const float* __restrict__ pbw, int n_vox, int C, fl
     for (int i = tid; i < n_vox; i += nth) dist[i] = pbw[(long long)i * C + (C - 1)];
 }
 
-// coarse minimum grid of the compact distance volume (one thread per coarse cell, 125 voxels each)
-__global__ void k_frame_coarse(const float* __restrict__ dist, int D, int H, int W, float* __restrict__ cmin) {
+// coarse minimum grid of the compact distance volume: one WARP per coarse cell, the lanes share out the up to 6^3 voxels
+// nvr_coarse_min visits (same set, same NaN rule: a NaN voxel poisons the cell), then a shuffle minimum
+__global__ void __launch_bounds__(128)
+k_frame_coarse(const float* __restrict__ dist, int D, int H, int W, float* __restrict__ cmin) {
     const int cD = nvr_coarse_dim(D), cH = nvr_coarse_dim(H), cW = nvr_coarse_dim(W);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cD * cH * cW; i += gridDim.x * blockDim.x)
-        cmin[i] = nvr_coarse_min(dist, D, H, W, i / (cH * cW), (i / cW) % cH, i % cW);
+    const int lane = threadIdx.x & 31;
+    const int n_cells = cD * cH * cW;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_cells; i += (gridDim.x * blockDim.x) >> 5) {
+        const int cz = i / (cH * cW), cy = (i / cW) % cH, cx = i % cW;
+        const int z0 = cz * NVR_CULL_B > 0 ? cz * NVR_CULL_B - 1 : 0, z1 = min(cz * NVR_CULL_B + NVR_CULL_B + 1, D - 1);
+        const int y0 = cy * NVR_CULL_B > 0 ? cy * NVR_CULL_B - 1 : 0, y1 = min(cy * NVR_CULL_B + NVR_CULL_B + 1, H - 1);
+        const int x0 = cx * NVR_CULL_B > 0 ? cx * NVR_CULL_B - 1 : 0, x1 = min(cx * NVR_CULL_B + NVR_CULL_B + 1, W - 1);
+        const int nz = z1 - z0 + 1, ny = y1 - y0 + 1, nx = x1 - x0 + 1;
+        float m = INFINITY;
+        bool nan = false;
+        for (int t = lane; t < nz * ny * nx; t += 32) {
+            const int z = z0 + t / (ny * nx), y = y0 + (t / nx) % ny, x = x0 + t % nx;
+            const float d = dist[((long long)z * H + y) * W + x];
+            nan |= d != d;
+            m = fminf(m, d);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, s));
+        nan = __any_sync(0xffffffffu, nan);
+        if (lane == 0) cmin[i] = nan ? __int_as_float(0x7fc00000) : m;
+    }
 }
 
 // Per-frame KNN acceleration structure, one CTA per part: a balanced KD partition of the part's posed

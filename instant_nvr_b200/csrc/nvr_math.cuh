@@ -240,6 +240,69 @@ NVR_HD void nvr_embed_point(const GridDev& g, const float x[3], float* out, int 
     }
 }
 
+
+#ifdef __CUDA_ARCH__
+// Device form of nvr_embed_point<2> in concat mode (the deformer grid: 8 levels x 2 features, 19 outputs): the same values
+// in the same order -- clamped corners, weights, accumulation over the corners c = 0..7 -- with 32-bit index arithmetic
+// (cvt.rzi + clamp == .long() + clamp, products < 2^40 reduced by nvr_mod_T40) and the 8 corner rows of a level fetched as
+// independent 8-byte loads before the first multiply (ncu r2a: the scalar form spent 17 % of k_warp's stall samples waiting
+// on one dependent row load after another and 14 % of its instructions on 64-bit row arithmetic).
+__device__ __forceinline__ void nvr_embed_point_f2_dev(const GridDev& g, const float x[3], float* out, int os) {
+    float u[3];
+    nvr_normalise(g, x, u);
+    out[0] = u[0]; out[os] = u[1]; out[2 * os] = u[2];
+    const bool fast_mod = g.T_magic40 != 0;
+    const unsigned int T32 = (unsigned int)g.T;
+#pragma unroll 1
+    for (int l = 0; l < g.n_levels; ++l) {
+        const int res = g.res[l];
+        const float size = g.size[l];
+        int i0[3], i1[3];
+        float o[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float f = u[a] / size;                             // :115 (IEEE fp32 divide)
+            i0[a] = min(max(__float2int_rz(f + 0.0f), 0), res - 1);  // :116-117
+            i1[a] = min(max(__float2int_rz(f + 1.0f), 0), res - 1);
+            o[a] = f - (float)i0[a];                                 // :118
+        }
+        unsigned int row[8];
+        const float2* tab;
+        if (l < g.start_hash) {
+            tab = reinterpret_cast<const float2*>(g.dense);
+            const unsigned int off = (unsigned int)g.dense_off[l];
+            const unsigned int ax[2] = {(unsigned int)(i0[0] * res * res) + off, (unsigned int)(i1[0] * res * res) + off};
+            const unsigned int ay[2] = {(unsigned int)(i0[1] * res), (unsigned int)(i1[1] * res)};
+            const unsigned int az[2] = {(unsigned int)i0[2], (unsigned int)i1[2]};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) row[c] = ax[(c >> 2) & 1] + ay[(c >> 1) & 1] + az[c & 1];
+        } else {
+            tab = reinterpret_cast<const float2*>(g.hash);
+            const unsigned int off = (unsigned int)(l - g.start_hash) * T32;
+            const unsigned long long hx[2] = {(unsigned long long)i0[0], (unsigned long long)i1[0]};
+            const unsigned long long hy[2] = {(unsigned long long)i0[1] * 19349663ull, (unsigned long long)i1[1] * 19349663ull};
+            const unsigned long long hz[2] = {(unsigned long long)i0[2] * 83492791ull, (unsigned long long)i1[2] * 83492791ull};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const unsigned long long h = hx[(c >> 2) & 1] ^ hy[(c >> 1) & 1] ^ hz[c & 1];
+                row[c] = (fast_mod ? nvr_mod_T40(h, T32, g.T_magic40) : (unsigned int)nvr_mod_T(h, g.T, g.T_magic)) + off;
+            }
+        }
+        float2 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + row[c]);
+        const float wx[2] = {1.0f - o[0], o[0]}, wy[2] = {1.0f - o[1], o[1]}, wz[2] = {1.0f - o[2], o[2]};
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float w = (wx[(c >> 2) & 1] * wy[(c >> 1) & 1]) * wz[c & 1];   // :158-159
+            a0 += w * v[c].x; a1 += w * v[c].y;                                    // :160
+        }
+        out[(3 + l * 2) * os] = a0; out[(3 + l * 2 + 1) * os] = a1;               // :169
+    }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------
 // trilinear volume lookup == F.grid_sample(bilinear, border, align_corners=True)
 //                                                     blend_utils.py:501-525, 528-555
@@ -561,17 +624,29 @@ NVR_HD void nvr_blend_lbs(const int idx[NVR_KNN], const float w[NVR_KNN], const 
     F2 M2[6], B2[6];                                              // element pairs (e, e+1): two FMAs per FFMA2
 #pragma unroll
     for (int e = 0; e < 6; ++e) { M2[e] = F2{0.0f, 0.0f}; B2[e] = F2{0.0f, 0.0f}; }
-#pragma unroll 2
-    for (int j = 0; j < NVR_JOINTS; ++j) {
-        const float bj = nvr_blend_joint(idx, w, pbw_part, j);
-        // skinning rows are sparse (<= 4 joints per vertex) and a warp's pairs are neighbours: most joints have zero
-        // weight for every lane, and adding 0 * A_j changes nothing
-        if (!NVR_ANY_ACTIVE(bj != 0.0f)) continue;
-        const F2 b2 = {bj, bj};
+    // joints four at a time: the neighbour rows are 24 contiguous floats (96 B, 16-byte aligned), so a quad of joints is ONE
+    // 16-byte load per neighbour instead of four 4-byte ones; per joint the sum over the neighbours keeps nvr_blend_joint's order
+#pragma unroll 1
+    for (int jq = 0; jq < NVR_JOINTS / 4; ++jq) {
+        float bq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int e = 0; e < 6; ++e) {
-            nvr_fma2(M2[e], b2, F2{A[j * 16 + 2 * e], A[j * 16 + 2 * e + 1]});
-            nvr_fma2(B2[e], b2, F2{bigA[j * 16 + 2 * e], bigA[j * 16 + 2 * e + 1]});
+        for (int i = 0; i < NVR_KNN; ++i) {
+            const float4 r = nvr_ld_vert(reinterpret_cast<const float4*>(pbw_part + (long long)idx[i] * NVR_JOINTS) + jq);
+            bq[0] += r.x * w[i]; bq[1] += r.y * w[i]; bq[2] += r.z * w[i]; bq[3] += r.w * w[i];      // :762
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const float bj = bq[jj];
+            const int j = jq * 4 + jj;
+            // skinning rows are sparse (<= 4 joints per vertex) and a warp's pairs are neighbours: most joints have zero
+            // weight for every lane, and adding 0 * A_j changes nothing
+            if (!NVR_ANY_ACTIVE(bj != 0.0f)) continue;
+            const F2 b2 = {bj, bj};
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+                nvr_fma2(M2[e], b2, F2{A[j * 16 + 2 * e], A[j * 16 + 2 * e + 1]});
+                nvr_fma2(B2[e], b2, F2{bigA[j * 16 + 2 * e], bigA[j * 16 + 2 * e + 1]});
+            }
         }
     }
     float M[12], B[12];
@@ -649,7 +724,11 @@ NVR_HD void nvr_deformer_point(const GridDev& g, const float* pk, const VolumeDe
     float uvt[3];
     nvr_sample_volume(tuv, x0, 0, 2, uvt);                        // pts_sample_uv :32
     uvt[2] = frame_dim;                                           // :35
-    nvr_embed_point<2>(g, uvt, sc, ss);                           // :37 (8 levels x 2 features, concat) -> sc[0..18]
+#ifdef __CUDA_ARCH__
+    nvr_embed_point_f2_dev(g, uvt, sc, ss);                       // :37 (8 levels x 2 features, concat) -> sc[0..18]
+#else
+    nvr_embed_point<2>(g, uvt, sc, ss);
+#endif
     {
         float e[20];
 #pragma unroll

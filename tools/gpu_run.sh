@@ -38,6 +38,10 @@ case "$stage" in
       NVR_TUNE=$t timeout 600 python bench.py --steps 20 --warmup 3 --no-extras > gpurun_out/ab_tune$t.json 2> gpurun_out/ab_tune$t.err
       echo "tune $t rc=$?"; python -c "import json,sys; d=json.load(open('gpurun_out/ab_tune$t.json')); print('tune $t', d['ms_per_step'], d['stage_ms_per_step'], d.get('embed_part_ms'))"
     done ;;
+  mode:*)
+    m="${stage#mode:}"
+    NVR_MLP_MODE=$m timeout 600 python bench.py --steps 20 --warmup 3 --no-extras > gpurun_out/ab_mode$m.json 2> gpurun_out/ab_mode$m.err
+    echo "mlp_mode $m rc=$?"; python -c "import json,sys; d=json.load(open('gpurun_out/ab_mode$m.json')); print('mlp_mode $m', d['ms_per_step'], d['stage_ms_per_step'], d.get('mlp_part_ms'))" ;;
   cfg:*)
     c="${stage#cfg:}"
     timeout 900 python bench.py --config $c --steps 5 --warmup 3 --no-extras > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "cfg $c rc=$?"; cut -c1-800 gpurun_out/bench_$c.json ;;
