@@ -113,8 +113,9 @@ typedef struct NvrConfig {
     int32_t abi_version;           /* NVR_ABI_VERSION */
     int32_t device;                /* CUDA device ordinal */
     float smpl_thresh;             /* cfg.smpl_thresh */
-    int32_t mlp_mode;              /* part MLPs: 0 fp32 FFMA tiles; 1 tcgen05 3xTF32 tiles, 256-thread CTAs; 2 the same with two
-                                      epilogue warpgroups per tile slot (512-thread CTAs) */
+    int32_t mlp_mode;              /* part MLPs: 0 fp32 FFMA tiles; 1 tcgen05 3xTF32 tiles, two tile slots, 256-thread CTAs; 2 the same with two
+                                      epilogue warpgroups per tile slot (512-thread CTAs); 3 tcgen05 kind::f16 with fp16-split operands
+                                      (hi + lo, three MMAs per product like 3xTF32, fp32-equivalent results), FOUR tile slots per SM */
     uint32_t tune;                 /* NVR_TUNE_* bits: occupancy variants of the same kernels (identical results) */
     uint32_t _pad;
 } NvrConfig;

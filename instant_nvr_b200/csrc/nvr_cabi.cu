@@ -15,6 +15,7 @@
 #include "nvr_kernels.cuh"
 #include "nvr_smpl.cuh"
 #include "nvr_mlp_tc.cuh"
+#include "nvr_mlp_f16.cuh"
 #include "nvr_train.cuh"
 #include "nvr_aux.cuh"
 
@@ -134,6 +135,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
         cudaFuncSetAttribute(k_cluster_verts, cudaFuncAttributeMaxDynamicSharedMemorySize, NVR_CLUSTER_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mlp_f16, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_deformer_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES) != cudaSuccess ||
         cudaMalloc(&h->d_part_mlp, NVR_PARTS * sizeof(PartMlpDev)) != cudaSuccess ||
@@ -336,10 +338,18 @@ static int embed_plan(const NvrEngine* h, int p, int begin[NVR_MAX_LEVELS], int 
     return n + 1;
 }
 
-// tensor-core part MLPs over one part's pair list; mlp_mode 1: one epilogue warpgroup per tile slot, 2: two
+// tensor-core part MLPs over one part's pair list; mlp_mode 3: fp16-split operands, four tile slots (nvr_mlp_f16.cuh);
+// 1 / 2: 3xTF32, two tile slots with one / two epilogue warpgroups each (nvr_mlp_tc.cuh)
+static size_t mlp_block_floats(const NvrEngine* h) { return h->cfg.mlp_mode == 3 ? (size_t)F16_BLOCK_FLOATS : (size_t)TC_BLOCK_FLOATS; }
+static void launch_mlp_prep(NvrEngine* h, cudaStream_t st) {
+    if (h->cfg.mlp_mode == 3) k_mlp_prep16<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
+    else k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
+}
 static void launch_mlp_tc(NvrEngine* h, int grid, const float* blk, int n_rgb, int part, const int* count, const PairRec* pl,
                           const float* el, float4* raws, int out_stride, cudaStream_t st) {
-    if (h->cfg.mlp_mode == 2)
+    if (h->cfg.mlp_mode == 3)
+        k_mlp_f16<<<grid, F16_THREADS, F16_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
+    else if (h->cfg.mlp_mode == 2)
         k_mlp_tc<2><<<grid, TC_THREADS(2), TC_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
     else
         k_mlp_tc<1><<<grid, TC_THREADS(1), TC_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
@@ -383,7 +393,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     const bool tc = h->cfg.mlp_mode >= 1;
     if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
         StageTimer t(h, st, NVR_STAGE_MLP);
-        k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
+        launch_mlp_prep(h, st);
         h->launches++;
     }
     for (int p = 0; p < NVR_NUM_PARTS; ++p) {
@@ -404,7 +414,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         } }
         StageTimer t(h, st, NVR_STAGE_MLP, p);
         if (tc)
-            launch_mlp_tc(h, grid_for(n, 256, sm), h->d_mlp_blocks + (size_t)p * TC_BLOCK_FLOATS, h->part_mlp[p].n_rgb, p,
+            launch_mlp_tc(h, grid_for(n, h->cfg.mlp_mode == 3 ? 128 * F16_SLOTS : 256, sm), h->d_mlp_blocks + (size_t)p * mlp_block_floats(h), h->part_mlp[p].n_rgb, p,
                           w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS, st);
         else
             k_mlp<<<grid_for(n, MLP_TILE, sm), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[p], p, h->fdev.latent_index,
@@ -666,8 +676,8 @@ extern "C" int nvr_part_mlp(NvrHandle h, int32_t part, const float* emb, const f
     k_make_pairs<<<(int)((n + 255) / 256), 256, 0, st>>>(dirs, (int)n, w.pairs, w.counters);
     if (h->cfg.mlp_mode >= 1) {
         if (((uintptr_t)emb & 15) != 0) return fail(h, "nvr_part_mlp: emb must be 16-byte aligned (rows of 20 floats)");
-        k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
-        launch_mlp_tc(h, grid_for(n, 256, h->sm_count), h->d_mlp_blocks + (size_t)part * TC_BLOCK_FLOATS, h->part_mlp[part].n_rgb, 0,
+        launch_mlp_prep(h, st);
+        launch_mlp_tc(h, grid_for(n, h->cfg.mlp_mode == 3 ? 128 * F16_SLOTS : 256, h->sm_count), h->d_mlp_blocks + (size_t)part * mlp_block_floats(h), h->part_mlp[part].n_rgb, 0,
                       w.counters, w.pairs, emb, (float4*)raw, 1, st);
         h->launches++;
     } else {

@@ -128,7 +128,7 @@ def test_part_mlp(gpu):
         assert err < 5e-6, (pid, err)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_part_mlp_tensor_core(gpu, mode):
     """The tcgen05 3xTF32 MLP kernel (mode 1: one epilogue warpgroup per tile slot, mode 2: two) against the fp32
     oracle (and against our fp32 FFMA kernel)."""
