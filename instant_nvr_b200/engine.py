@@ -29,7 +29,7 @@ def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
     return t
 
 
-DEFAULT_MLP_MODE = 1
+DEFAULT_MLP_MODE = 3
 DEFAULT_TUNE = 0
 
 
