@@ -35,11 +35,16 @@ __device__ __forceinline__ long long frame_index(const FrameOut& f, long long i)
 // is ordered before the flag by the kernel boundary plus the system-scope fence.
 struct FrameFlags { unsigned int* peer[NVR_MAX_RANKS]; };   // every rank's flag block (peer-mapped); peer[rank] is the local one
 __global__ void k_frame_barrier(FrameFlags ff, int world, int rank, unsigned int epoch) {
-    unsigned int* const local_flags = ff.peer[rank];
+    unsigned int* local_flags = nullptr;
+#pragma unroll
+    for (int r = 0; r < NVR_MAX_RANKS; ++r) local_flags = rank == r ? ff.peer[r] : local_flags;
     const int lane = threadIdx.x;
     __threadfence_system();
     if (lane < world) {
-        unsigned int* dst = ff.peer[lane] + rank * NVR_FRAME_FLAG_STRIDE;
+        unsigned int* peer = nullptr;
+#pragma unroll
+        for (int r = 0; r < NVR_MAX_RANKS; ++r) peer = lane == r ? ff.peer[r] : peer;
+        unsigned int* dst = peer + rank * NVR_FRAME_FLAG_STRIDE;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
         const unsigned int* src = local_flags + lane * NVR_FRAME_FLAG_STRIDE;
         unsigned int v;
@@ -58,6 +63,8 @@ __global__ void k_frame_scatter(FrameOut f, const float* __restrict__ rgb, const
         const long long gi = frame_index(f, i);
         if (gi >= f.n_total) continue;
         const float4 v = make_float4(rgb[i * 3], rgb[i * 3 + 1], rgb[i * 3 + 2], acc[i]);
-        for (int r = 0; r < f.world; ++r) f.slot[r][gi] = v;
+#pragma unroll
+        for (int r = 0; r < NVR_MAX_RANKS; ++r)
+            if (r < f.world) f.slot[r][gi] = v;
     }
 }

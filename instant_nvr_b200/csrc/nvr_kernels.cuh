@@ -1096,7 +1096,10 @@ k_resolve_rays(const int* __restrict__ surv_of_sample, const float4* __restrict_
         }
         if (lane < fo.world) {
             const long long gi = frame_index(fo, ray_base + ray);
-            if (gi < fo.n_total) fo.slot[lane][gi] = make_float4(cr, cg, cb, ca);
+            float4* dst = nullptr;                                  // static indices only: a dynamic one would copy the
+#pragma unroll                                                      // parameter array to the stack
+            for (int r = 0; r < NVR_MAX_RANKS; ++r) dst = lane == r ? fo.slot[r] : dst;
+            if (gi < fo.n_total) dst[gi] = make_float4(cr, cg, cb, ca);
         }
     }
 }
