@@ -38,6 +38,7 @@ struct NvrEngine {
     int* d_perm = nullptr; size_t perm_cap = 0;            // KD partition: cluster slot -> vertex index in its part
     long long perm_key = 0; int perm_maxlen = 0;           // topology the partition was built for
     PartMlpDev* d_part_mlp = nullptr;       // device copy of part_mlp[] for k_mlp_prep
+    GridDev* d_part_grid = nullptr;         // device copy of part_grid[] for k_embed_parts
     float* d_mlp_blocks = nullptr;          // NVR_PARTS packed tcgen05 parameter blocks (mlp_mode 1)
     float* d_presum = nullptr; size_t presum_cap = 0;     // inference tables: per part [dense rows | hash rows] sums
     size_t presum_off[NVR_PARTS + 1] = {0};
@@ -139,6 +140,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
         cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_deformer_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, DB_SMEM_BYTES) != cudaSuccess ||
         cudaMalloc(&h->d_part_mlp, NVR_PARTS * sizeof(PartMlpDev)) != cudaSuccess ||
+        cudaMalloc(&h->d_part_grid, NVR_PARTS * sizeof(GridDev)) != cudaSuccess ||
         cudaMalloc(&h->d_mlp_blocks, (size_t)NVR_PARTS * TC_BLOCK_FLOATS * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
         delete h;
@@ -151,7 +153,7 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
 extern "C" int nvr_destroy(NvrHandle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_perm); cudaFree(h->d_part_mlp); cudaFree(h->d_mlp_blocks); cudaFree(h->d_presum); cudaFree(h->d_counters_snapshot);
+    cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_perm); cudaFree(h->d_part_mlp); cudaFree(h->d_part_grid); cudaFree(h->d_mlp_blocks); cudaFree(h->d_presum); cudaFree(h->d_counters_snapshot);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
     frame_release(h);
@@ -201,6 +203,7 @@ extern "C" int nvr_bind_params(NvrHandle h, const NvrParams* p) {
                              p->deformer_mlp[1].bias, p->deformer_mlp[2].weight, p->deformer_mlp[2].bias};
     NVR_CHECK(h, cudaSetDevice(h->cfg.device));
     NVR_CHECK(h, cudaMemcpy(h->d_part_mlp, h->part_mlp, sizeof(h->part_mlp), cudaMemcpyHostToDevice));
+    NVR_CHECK(h, cudaMemcpy(h->d_part_grid, h->part_grid, sizeof(h->part_grid), cudaMemcpyHostToDevice));
     h->have_params = true;
     h->presum_valid = false;                 // new storages: the inference tables must be rebuilt
     return 0;
@@ -347,9 +350,12 @@ static void launch_mlp_prep(NvrEngine* h, cudaStream_t st) {
 }
 static void launch_mlp_tc(NvrEngine* h, int grid, const float* blk, int n_rgb, int part, const int* count, const PairRec* pl,
                           const float* el, float4* raws, int out_stride, cudaStream_t st) {
-    if (h->cfg.mlp_mode == 3)
-        k_mlp_f16<<<grid, F16_THREADS, F16_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
-    else if (h->cfg.mlp_mode == 2)
+    if (h->cfg.mlp_mode == 3) {
+        MlpBatch mb;
+        memset(&mb, 0, sizeof(mb));
+        mb.blk[0] = blk; mb.count[0] = count; mb.pl[0] = pl; mb.el[0] = el; mb.n_rgb[0] = n_rgb; mb.out_part[0] = part; mb.n_parts = 1;
+        k_mlp_f16<<<grid, F16_THREADS, F16_SMEM_BYTES, st>>>(mb, raws, out_stride);
+    } else if (h->cfg.mlp_mode == 2)
         k_mlp_tc<2><<<grid, TC_THREADS(2), TC_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
     else
         k_mlp_tc<1><<<grid, TC_THREADS(1), TC_SMEM_BYTES, st>>>(blk, n_rgb, part, count, pl, el, raws, out_stride);
@@ -396,11 +402,26 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         launch_mlp_prep(h, st);
         h->launches++;
     }
+    // Stage timing (nvr_profile) keeps one gather + one MLP launch per part, so the per-part event times exist; otherwise the five
+    // gathers go out as one grid (blockIdx.y = part: the parts' launch tails overlap) and the five MLPs as one balanced launch
+    const bool merged = !h->profiling && !(h->cfg.tune & NVR_TUNE_SERIAL);
+    const bool presum = h->presum_valid && !full_tables;
+    if (merged && !presum && !(h->cfg.tune & NVR_TUNE_LEVEL_MAJOR)) {
+        EmbedBatch eb;
+        for (int p = 0; p < NVR_NUM_PARTS; ++p) {
+            eb.x[p] = (const float*)(w.pairs + (long long)p * w.cap);
+            eb.count[p] = w.counters + NVR_CTR_PAIR + p;
+            eb.out[p] = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
+        }
+        k_embed_parts<<<dim3(grid_for(n, 128, sm * 2), NVR_NUM_PARTS), 256, 0, st>>>(h->d_part_grid, eb, 8, NVR_EMB_STRIDE);
+        h->launches -= NVR_NUM_PARTS - 1;
+    }
     for (int p = 0; p < NVR_NUM_PARTS; ++p) {
         const PairRec* pl = w.pairs + (long long)p * w.cap;
         float* el = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
-        { StageTimer t(h, st, NVR_STAGE_EMBED, p);
-        if (h->presum_valid && !full_tables) {
+        if (!(merged && !presum && !(h->cfg.tune & NVR_TUNE_LEVEL_MAJOR))) {
+        StageTimer t(h, st, NVR_STAGE_EMBED, p);
+        if (presum) {
             const float* sd = h->d_presum + h->presum_off[p];
             k_embed_presum<<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->part_grid[p], sd, sd + dense_rows(h->params.part[p].grid), (const float*)pl, 8,
                                                                     w.counters + NVR_CTR_PAIR + p, 0, el, NVR_EMB_STRIDE);
@@ -412,6 +433,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
                                                                  el, NVR_EMB_STRIDE, lb[i], le[i]);
             h->launches += n_slices - 1;
         } }
+        if (merged && h->cfg.mlp_mode == 3) continue;
         StageTimer t(h, st, NVR_STAGE_MLP, p);
         if (tc)
             launch_mlp_tc(h, grid_for(n, h->cfg.mlp_mode == 3 ? 128 * F16_SLOTS : 256, sm), h->d_mlp_blocks + (size_t)p * mlp_block_floats(h), h->part_mlp[p].n_rgb, p,
@@ -419,6 +441,18 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
         else
             k_mlp<<<grid_for(n, MLP_TILE, sm), 256, MLP_SMEM_BYTES, st>>>(h->part_mlp[p], p, h->fdev.latent_index,
                                                                           w.counters + NVR_CTR_PAIR + p, pl, el, w.raws, NVR_NUM_PARTS);
+    }
+    if (merged && h->cfg.mlp_mode == 3) {
+        MlpBatch mb;
+        memset(&mb, 0, sizeof(mb));
+        for (int p = 0; p < NVR_NUM_PARTS; ++p) {
+            mb.blk[p] = h->d_mlp_blocks + (size_t)p * F16_BLOCK_FLOATS; mb.count[p] = w.counters + NVR_CTR_PAIR + p;
+            mb.pl[p] = w.pairs + (long long)p * w.cap; mb.el[p] = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
+            mb.n_rgb[p] = h->part_mlp[p].n_rgb; mb.out_part[p] = p;
+        }
+        mb.n_parts = NVR_NUM_PARTS;
+        k_mlp_f16<<<grid_for(n, 128 * F16_SLOTS / 2, sm), F16_THREADS, F16_SMEM_BYTES, st>>>(mb, w.raws, NVR_NUM_PARTS);
+        h->launches -= NVR_NUM_PARTS - 1;
     }
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 3 + 2 * NVR_NUM_PARTS;

@@ -25,6 +25,7 @@
 #define NVR_CTR_SURV 0
 #define NVR_CTR_PAIR 1             // [1..5]
 #define NVR_CTR_FAR 6              // [6..10] flagged pairs answered by the part's shared far-field pair
+#define NVR_CTR_WORK 11             // k_knn's dynamic work-unit counter
 #define NVR_CTR_WORDS 16
 // Far-field pairs.  A part farther than ~0.73 m from a sample still gets flagged (its Gaussian weights sum to far less
 // than the 1e-8 in the normalisation, so pdist -> 0 < smpl_thresh: DESIGN.md section 1).  Once sum(w) < NVR_FAR_WSUM the
@@ -491,9 +492,18 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
         rec.surv = far_slot; rec._pad[0] = rec._pad[1] = rec._pad[2] = 0;
         recs[(long long)part * cap + atomicAdd(&counters[NVR_CTR_PAIR + part], 1)] = rec;
     }
-    // warp-uniform trip count so the ballots below see full warps
-    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_surv; base += gridDim.x * blockDim.x) {
-        const int s = base + lane;
+    // Work unit = (32 consecutive survivors, ONE part), handed out through a device counter: a part search costs anything
+    // from a box test (far-field / certainly unflagged) to a dozen cluster scans, so a static grid-stride split leaves the
+    // launch waiting for its unluckiest warp -- visibly so when a pass holds only a few survivors per warp slot (an 8-GPU
+    // shard of a 512 x 512 frame: 310 k survivors over 4736 warp slots).  DENSE keeps all five parts in one warp (arg-min).
+    const int n_units = ((n_surv + 31) / 32) * (DENSE ? 1 : NVR_PARTS);
+    while (true) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(&counters[NVR_CTR_WORK], 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const int s = (DENSE ? unit : unit / NVR_PARTS) * 32 + lane;
+        const int unit_part = DENSE ? 0 : unit % NVR_PARTS;
         const bool live = s < n_surv;
         float p[3] = {0.f, 0.f, 0.f};
         int sample = 0;
@@ -547,8 +557,8 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
                 if (flag) recs[(long long)part * cap + wbase + __popc(ballot & ((1u << lane) - 1u))] = best;
             }
         } else {
-#pragma unroll 1
-        for (int part = 0; part < NVR_PARTS; ++part) {
+        {
+            const int part = unit_part;
             Knn4 k;
             nvr_knn_init(k);
             const int group = knn_part_group(fr, part, p, live, qlo, qhi, k, far_slot >= 0, thresh);
@@ -721,12 +731,8 @@ __device__ __forceinline__ const float* level_rows(const GridDev& g, int l, int 
     return g.hash;
 }
 
-__global__ void __launch_bounds__(256, 2)
-k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
-        float* __restrict__ eb, int emb_stride, int l_begin, int l_end) {
-    // levels [l_begin, l_end) only (the normalised coordinates are written by the launch with l_begin == 0): a part whose
-    // tables exceed the L2 is gathered LEVEL-MAJOR, one launch per L2-sized slice of its tables (nvr_cabi.cu, embed_plan)
-    const int n = count_dev ? *count_dev : n_imm;
+__device__ __forceinline__ void embed_body(const GridDev& g, const float* __restrict__ xb, int xstride, int n,
+                                           float* __restrict__ eb, int emb_stride, int l_begin, int l_end) {
     const int lane = threadIdx.x & 31, half = lane & 1;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool fast_mod = g.T_magic40 != 0;
@@ -769,6 +775,40 @@ k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restr
             if (live && half == (l & 1)) o[3 + l] = sfeat;
         }
     }
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restrict__ count_dev, int n_imm,
+        float* __restrict__ eb, int emb_stride, int l_begin, int l_end) {
+    // levels [l_begin, l_end) only (the normalised coordinates are written by the launch with l_begin == 0): the level-major
+    // experiment gathers a part one L2-sized slice of its tables per launch (nvr_cabi.cu, embed_plan)
+    embed_body(g, xb, xstride, count_dev ? *count_dev : n_imm, eb, emb_stride, l_begin, l_end);
+}
+
+// All five parts of a pass as ONE grid: blockIdx.y = part.  Same per-CTA work as five k_embed launches (a CTA gathers one part's
+// pairs, so consecutive units still share coarse-level rows in L1), but the launches' tails overlap: CTAs of part p + 1 start as
+// the last CTAs of part p drain.  The part's grid description is staged in shared memory (a run-time index into a kernel
+// parameter array would be copied to the stack).
+struct EmbedBatch { const float* x[NVR_PARTS]; const int* count[NVR_PARTS]; float* out[NVR_PARTS]; };
+__global__ void __launch_bounds__(256, 2)
+k_embed_parts(const GridDev* __restrict__ grids, EmbedBatch b, int xstride, int emb_stride) {
+    __shared__ GridDev sg;
+    __shared__ const float* s_x;
+    __shared__ const int* s_count;
+    __shared__ float* s_out;
+    const int part = blockIdx.y;
+    {
+        const int* src = reinterpret_cast<const int*>(grids + part);
+        int* dst = reinterpret_cast<int*>(&sg);
+        for (int i = threadIdx.x; i < (int)(sizeof(GridDev) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int p = 0; p < NVR_PARTS; ++p)
+                if (p == part) { s_x = b.x[p]; s_count = b.count[p]; s_out = b.out[p]; }
+        }
+    }
+    __syncthreads();
+    embed_body(sg, s_x, xstride, *s_count, s_out, emb_stride, 0, sg.n_levels);
 }
 
 // -----------------------------------------------------------------------------------------

@@ -182,26 +182,36 @@ __device__ __forceinline__ void store_split_h(uint32_t t_hi, uint32_t t_lo, cons
     }
 }
 
-// One launch per part.  blk = that part's packed block (k_mlp_prep16); pl / el = its pair list and embedding rows.
+// Work of one launch: the pair lists of n_parts parts (one part: the stand-alone entry point; five: a render pass).  All tiles
+// of all parts form ONE index space dealt round-robin to the (CTA, slot) pairs, so a launch is balanced whatever the parts'
+// sizes, and a CTA walks its tiles part by part, reloading the 54 KB parameter block at each part boundary.
+struct MlpBatch {
+    const float* blk[NVR_PARTS];          // packed parameter block of each part (k_mlp_prep16)
+    const int* count[NVR_PARTS];          // device-side list lengths
+    const PairRec* pl[NVR_PARTS];
+    const float* el[NVR_PARTS];
+    int n_rgb[NVR_PARTS];
+    int out_part[NVR_PARTS];              // column of `raws` the part's results go to
+    int n_parts;
+};
+
 __global__ void __launch_bounds__(F16_THREADS, 1)
-k_mlp_f16(const float* __restrict__ blk, int n_rgb, int part, const int* __restrict__ count_dev, const PairRec* __restrict__ pl,
-          const float* __restrict__ el, float4* __restrict__ raws, int out_stride) {
+k_mlp_f16(const MlpBatch mb_param, float4* __restrict__ raws, int out_stride) {
     extern __shared__ __align__(128) unsigned char smb[];
+    __shared__ MlpBatch mb;                                           // indexed by a run-time part below: a copy in shared
+    if (threadIdx.x == 0) mb = mb_param;                              // memory, not a stack copy of the parameter
+    __syncthreads();
     float* smf = reinterpret_cast<float*>(smb);
-    const int n = *count_dev;
-    const int n_tiles = (n + 127) / 128;
-    if ((int)blockIdx.x * F16_SLOTS >= n_tiles) return;               // block-uniform, before any allocation
     uint64_t* bars = reinterpret_cast<uint64_t*>(smb + F16_SM_BAR);
     uint32_t* tbase_slot = reinterpret_cast<uint32_t*>(smb + F16_SM_BAR + 40);
     const int tid = threadIdx.x, warp = tid >> 5, slot = warp >> 2, stid = tid & 127;
-    {   // parameter block -> shared memory (16-byte copies; the block is 16-byte aligned by construction)
-        const float4* src = reinterpret_cast<const float4*>(blk);
-        float4* dst = reinterpret_cast<float4*>(smb);
-        for (int i = tid; i < F16_BLOCK_FLOATS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
+    int tiles_before = 0, total_tiles = 0;
+#pragma unroll
+    for (int p = 0; p < NVR_PARTS; ++p)
+        if (p < mb.n_parts) total_tiles += (*mb.count[p] + 127) / 128;
+    if ((int)blockIdx.x * F16_SLOTS >= total_tiles) return;           // block-uniform, before any allocation
     if (warp == 0) tmem_alloc(smem_u32(tbase_slot), 512);
     if (tid < F16_SLOTS) mbar_init(smem_u32(bars + tid), 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy panel writes -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -217,10 +227,36 @@ k_mlp_f16(const float* __restrict__ blk, int n_rgb, int part, const int* __restr
     const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
     const float* b0 = smf + F16_F_B0; const float* b2 = smf + F16_F_B2; const float* b3 = smf + F16_F_B3;
     const float* w1 = smf + F16_F_W1; const float* w4 = smf + F16_F_W4; const float* sc = smf + F16_F_SC;
-    const bool three = n_rgb == 3;
     uint32_t phase = 0;
+    const int stride = gridDim.x * F16_SLOTS, mine = blockIdx.x * F16_SLOTS + slot;   // global tile g belongs to slot g % stride
 
-    for (int tile = blockIdx.x * F16_SLOTS + slot; tile < n_tiles; tile += gridDim.x * F16_SLOTS) {
+#pragma unroll 1
+    for (int pi = 0; pi < mb.n_parts; ++pi) {
+    const int n = *mb.count[pi];
+    const int n_tiles = (n + 127) / 128;
+    // global tile tiles_before + t belongs to slot (tiles_before + t) % stride: the first tile of this part owned by
+    // (this CTA, slot s) is t0(s); the CTA takes part in the part iff one of its four slots owns a tile
+    bool cta_has = false;
+#pragma unroll
+    for (int sl = 0; sl < F16_SLOTS; ++sl)
+        cta_has |= (((int)blockIdx.x * F16_SLOTS + sl - tiles_before) % stride + stride) % stride < n_tiles;
+    const int t0 = ((mine - tiles_before) % stride + stride) % stride;
+    tiles_before += n_tiles;
+    if (!cta_has) continue;                                           // block-uniform
+    __syncthreads();                                                  // every slot is done with the previous part's panels
+    {   // parameter block -> shared memory (16-byte copies; the block is 16-byte aligned by construction)
+        const float4* src = reinterpret_cast<const float4*>(mb.blk[pi]);
+        float4* dst = reinterpret_cast<float4*>(smb);
+        for (int i = tid; i < F16_BLOCK_FLOATS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy panel writes -> visible to the tensor core
+    __syncthreads();
+    const bool three = mb.n_rgb[pi] == 3;
+    const int part = mb.out_part[pi];
+    const PairRec* __restrict__ pl = mb.pl[pi];
+    const float* __restrict__ el = mb.el[pi];
+
+    for (int tile = t0; tile < n_tiles; tile += stride) {
         const int row = tile * 128 + stid;
         const int pr = min(row, n - 1);
         int surv;
@@ -322,6 +358,7 @@ k_mlp_f16(const float* __restrict__ blk, int n_rgb, int part, const int* __restr
         }
         if (row < n)
             raws[(long long)surv * out_stride + part] = make_float4(nvr_sigmoid(r[0]), nvr_sigmoid(r[1]), nvr_sigmoid(r[2]), occ);
+    }
     }
     tc_fence_before();
     __syncthreads();
