@@ -627,6 +627,27 @@ def main():
            "note": "k_knn / k_warp are FP32-ALU + issue bound (ncu: 68 % / 59 % issue-active); the deformer MLP is 3456 FLOP per pair "
                    "(SURVEY.md 8(d)); fractions are of 148 SMs x 128 lanes x 2 FLOP x SM clock"}
 
+    # ---- N > 1: the frame every rank assembled must BE the single-GPU frame (rays are independent): rank 0 renders the whole
+    #      frame alone and every rank compares its assembled copy bit for bit (the check tests/test_gpu_multi.py makes, here
+    #      inside the scaling run itself)
+    frame_check = None
+    if world > 1:
+        try:
+            from instant_nvr_b200.synthetic import make_rays
+            assembled = wl.step_device().clone()
+            full = make_rays(frame, cfgd["H"], cfgd["W"], drop_missing=True)
+            ref = torch.empty(wl.n_total, 4, device="cuda")
+            if rank == 0:
+                fr = {k: full[k][0].cuda() for k in ("ray_o", "ray_d", "near", "far")}
+                r_rgb, r_acc = eng.render_rays(fr["ray_o"], fr["ray_d"], fr["near"], fr["far"], cfgd["S"])
+                ref = torch.cat([r_rgb, r_acc[:, None]], 1).contiguous()
+            dist.broadcast(ref, 0)
+            ok = torch.tensor([int(torch.equal(assembled[:, :4], ref))], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            frame_check = {"assembled_frame_equals_single_gpu_render_bitwise_on_every_rank": bool(ok.item()),
+                           "max_abs_diff_rank0": float((assembled[:, :4] - ref).abs().max().item()), "rays": wl.n_total}
+        except Exception as ex:
+            frame_check = {"error": f"{type(ex).__name__}: {ex}"}
     extras = {}
     wl.close()                                       # one peer frame buffer per engine: the supplementary workloads bring their own
     if not args.no_extras:
@@ -740,6 +761,7 @@ def main():
                           f"({ms_prof / p_steps:.3f} ms/step in that mode); the headline steps run without the events",
             "embed_part_ms": [per(v) for v in prof["embed_part_ms"]], "mlp_part_ms": [per(v) for v in prof["mlp_part_ms"]],
             "csrc_hash": csrc_hash(),
+            "frame_check": frame_check,
             "cpu_baseline": extras.pop("cpu_baseline", None),
         }
         line.update(extras)

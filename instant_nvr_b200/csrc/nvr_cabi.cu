@@ -345,7 +345,7 @@ static int embed_plan(const NvrEngine* h, int p, int begin[NVR_MAX_LEVELS], int 
 // 1 / 2: 3xTF32, two tile slots with one / two epilogue warpgroups each (nvr_mlp_tc.cuh)
 static size_t mlp_block_floats(const NvrEngine* h) { return h->cfg.mlp_mode == 3 ? (size_t)F16_BLOCK_FLOATS : (size_t)TC_BLOCK_FLOATS; }
 static void launch_mlp_prep(NvrEngine* h, cudaStream_t st) {
-    if (h->cfg.mlp_mode == 3) k_mlp_prep16<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
+    if (h->cfg.mlp_mode == 3) k_mlp_prep16<<<dim3(NVR_NUM_PARTS, F16_PREP_SPLIT), 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
     else k_mlp_prep<<<NVR_NUM_PARTS, 256, 0, st>>>(h->d_part_mlp, h->fdev.latent_index, h->d_mlp_blocks);
 }
 static void launch_mlp_tc(NvrEngine* h, int grid, const float* blk, int n_rgb, int part, const int* count, const PairRec* pl,

@@ -47,8 +47,11 @@
 #define F16_SLOTS 4
 #define F16_XPANEL_BYTES (F16_KX * 128 * 2)                          // one hi OR lo X panel: [6 chunks][128 rows][16 B]
 #define F16_SM_X (F16_BLOCK_FLOATS * 4)                              // byte offset of the X panels: [slot][hi|lo]
-#define F16_SM_BAR (F16_SM_X + F16_SLOTS * 2 * F16_XPANEL_BYTES)     // 4 mbarriers + tmem base
-#define F16_SMEM_BYTES (F16_SM_BAR + 64)
+#define F16_STAGE_E_BYTES (128 * NVR_EMB_STRIDE * 4)                 // one tile's embedding rows (128 x 80 B, contiguous in HBM)
+#define F16_STAGE_BYTES (F16_STAGE_E_BYTES + 128 * 32)               // + its pair records (128 x 32 B)
+#define F16_SM_STAGE (F16_SM_X + F16_SLOTS * 2 * F16_XPANEL_BYTES)   // [slot] raw input rows of the slot's NEXT tile (TMA bulk copies)
+#define F16_SM_BAR (F16_SM_STAGE + F16_SLOTS * F16_STAGE_BYTES)      // mbarriers: 4 MMA + 4 stage-full + 1 parameter block; tmem base
+#define F16_SMEM_BYTES (F16_SM_BAR + 96)
 #define F16_SLOT_COLS 128
 #define F16_COL_H 0
 #define F16_COL_D 64
@@ -64,6 +67,9 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {      // a -> bit
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// grid (5 parts, F16_PREP_SPLIT): blockIdx.y takes every F16_PREP_SPLIT-th output row n, so the packing (the 64 x 64 x 16
+// product M = W2f W1f above all) is spread over 80 CTAs instead of 5 -- it sits on the critical path of every pass
+#define F16_PREP_SPLIT 16
 __global__ void __launch_bounds__(256)
 k_mlp_prep16(const PartMlpDev* __restrict__ parts, const long long* __restrict__ latent_index, float* __restrict__ blocks) {
     const PartMlpDev pm = parts[blockIdx.x];
@@ -77,6 +83,7 @@ k_mlp_prep16(const PartMlpDev* __restrict__ parts, const long long* __restrict__
     long long li = latent_index[0];
     li = li < 0 ? 0 : (li >= pm.n_latent ? pm.n_latent - 1 : li);
     const float* lat = pm.latent + li * 8;
+    const int ny = gridDim.y, y = blockIdx.y, rows = (64 - y + ny - 1) / ny;   // this CTA's rows: n = y + j ny, j < rows
     auto put = [&](int off, int K, int n, int k, float w) {              // element (n, k) of a [K/8][64][8] panel pair
         float h, l;
         split11(w, h, l);
@@ -84,32 +91,33 @@ k_mlp_prep16(const PartMlpDev* __restrict__ parts, const long long* __restrict__
         hb[off + idx] = __float2half_rn(h);
         hb[off + F16_PANEL_HALVES(K) + idx] = __float2half_rn(l);
     };
-    for (int i = threadIdx.x; i < 64 * F16_K0; i += blockDim.x) {
-        const int n = i / F16_K0, k = i - n * F16_K0;
+    for (int i = threadIdx.x; i < rows * F16_K0; i += blockDim.x) {
+        const int n = y + (i / F16_K0) * ny, k = i % F16_K0;
         put(F16_OFF_P0, F16_K0, n, k, k < 19 ? W0[n * 19 + k] : 0.0f);
     }
-    for (int i = threadIdx.x; i < 64 * F16_KX; i += blockDim.x) {
-        const int n = i / F16_KX, k = i - n * F16_KX;
+    for (int i = threadIdx.x; i < rows * F16_KX; i += blockDim.x) {
+        const int n = y + (i / F16_KX) * ny, k = i % F16_KX;
         put(F16_OFF_PX, F16_KX, n, k, k < 46 ? W2[n * 70 + k] : 0.0f);
     }
-    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
-        const int n = i >> 6, k = i & 63;
+    for (int i = threadIdx.x; i < rows * 64; i += blockDim.x) {
+        const int n = y + (i >> 6) * ny, k = i & 63;
         float m = 0.0f;                                                 // M = W2f W1f
         for (int j = 0; j < 16; ++j) m += W2[n * 70 + 46 + j] * W1[(1 + j) * 64 + k];
         put(F16_OFF_PM, F16_KH, n, k, m);
         put(F16_OFF_P3, F16_KH, n, k, three ? W3[n * 64 + k] : 0.0f);
     }
-    for (int n = threadIdx.x; n < 64; n += blockDim.x) {
+    for (int j = threadIdx.x; j < rows; j += blockDim.x) {
+        const int n = y + j * ny;
         blk[F16_F_B0 + n] = pm.occ[0].b[n];
         float b = pm.rgb[0].b[n];
-        for (int j = 0; j < 16; ++j) b += W2[n * 70 + 46 + j] * pm.occ[1].b[1 + j];
+        for (int q = 0; q < 16; ++q) b += W2[n * 70 + 46 + q] * pm.occ[1].b[1 + q];
         for (int c = 0; c < 8; ++c) b += W2[n * 70 + 62 + c] * lat[c];
         blk[F16_F_B2 + n] = b;
         blk[F16_F_B3 + n] = three ? pm.rgb[1].b[n] : 0.0f;
         blk[F16_F_W1 + n] = W1[n];
-        for (int j = 0; j < 3; ++j) blk[F16_F_W4 + j * 64 + n] = W4[j * 64 + n];
+        for (int q = 0; q < 3; ++q) blk[F16_F_W4 + q * 64 + n] = W4[q * 64 + n];
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && y == 0) {
         blk[F16_F_SC] = pm.occ[1].b[0];
         for (int j = 0; j < 3; ++j) blk[F16_F_SC + 1 + j] = pm.rgb[pm.n_rgb - 1].b[j];
     }
@@ -162,6 +170,16 @@ __device__ __forceinline__ void gemm3h_ts(uint32_t d, uint32_t a_hi, uint32_t a_
     }
 }
 
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP): `bytes` (a multiple of 16) from global to shared memory, completion counted on an
+// mbarrier in transaction bytes.  One thread issues it; nobody's registers or LSU slots are tied up while the data is in flight.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void slot_sync128(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 
 // 64 activations of one row -> the hi / lo halves of the next A operand in tensor memory (32 + 32 packed columns)
@@ -203,7 +221,7 @@ k_mlp_f16(const MlpBatch mb_param, float4* __restrict__ raws, int out_stride) {
     __syncthreads();
     float* smf = reinterpret_cast<float*>(smb);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smb + F16_SM_BAR);
-    uint32_t* tbase_slot = reinterpret_cast<uint32_t*>(smb + F16_SM_BAR + 40);
+    uint32_t* tbase_slot = reinterpret_cast<uint32_t*>(smb + F16_SM_BAR + 80);
     const int tid = threadIdx.x, warp = tid >> 5, slot = warp >> 2, stid = tid & 127;
     int tiles_before = 0, total_tiles = 0;
 #pragma unroll
@@ -211,11 +229,15 @@ k_mlp_f16(const MlpBatch mb_param, float4* __restrict__ raws, int out_stride) {
         if (p < mb.n_parts) total_tiles += (*mb.count[p] + 127) / 128;
     if ((int)blockIdx.x * F16_SLOTS >= total_tiles) return;           // block-uniform, before any allocation
     if (warp == 0) tmem_alloc(smem_u32(tbase_slot), 512);
-    if (tid < F16_SLOTS) mbar_init(smem_u32(bars + tid), 1);
+    if (tid < 2 * F16_SLOTS + 1) mbar_init(smem_u32(bars + tid), 1);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tbase_slot + (uint32_t)slot * F16_SLOT_COLS;
+    const uint32_t bar_full = smem_u32(bars + F16_SLOTS + slot), bar_w = smem_u32(bars + 2 * F16_SLOTS);
+    unsigned char* stage = smb + F16_SM_STAGE + slot * F16_STAGE_BYTES;
+    const uint32_t s_stage = smem_u32(stage);
+    uint32_t phase_full = 0, phase_w = 0;
     const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
     const uint32_t bar_a = smem_u32(bars + slot);
     unsigned char* x_hi = smb + F16_SM_X + slot * 2 * F16_XPANEL_BYTES;
@@ -244,34 +266,42 @@ k_mlp_f16(const MlpBatch mb_param, float4* __restrict__ raws, int out_stride) {
     tiles_before += n_tiles;
     if (!cta_has) continue;                                           // block-uniform
     __syncthreads();                                                  // every slot is done with the previous part's panels
-    {   // parameter block -> shared memory (16-byte copies; the block is 16-byte aligned by construction)
-        const float4* src = reinterpret_cast<const float4*>(mb.blk[pi]);
-        float4* dst = reinterpret_cast<float4*>(smb);
-        for (int i = tid; i < F16_BLOCK_FLOATS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy panel writes -> visible to the tensor core
-    __syncthreads();
-    const bool three = mb.n_rgb[pi] == 3;
-    const int part = mb.out_part[pi];
     const PairRec* __restrict__ pl = mb.pl[pi];
     const float* __restrict__ el = mb.el[pi];
+    // tile t's input rows -> the slot's staging buffer: two bulk copies (embedding rows, pair records) on the slot's "full" barrier
+    auto prefetch = [&](int t) {
+        const uint32_t rows = (uint32_t)min(128, n - t * 128);
+        mbar_expect_tx(bar_full, rows * (NVR_EMB_STRIDE * 4 + 32));
+        bulk_g2s(s_stage, el + (size_t)t * 128 * NVR_EMB_STRIDE, rows * NVR_EMB_STRIDE * 4, bar_full);
+        bulk_g2s(s_stage + F16_STAGE_E_BYTES, pl + (size_t)t * 128, rows * 32, bar_full);
+    };
+    if (tid == 0) {   // parameter block -> shared memory: ONE 54 KB bulk copy
+        mbar_expect_tx(bar_w, F16_BLOCK_FLOATS * 4);
+        bulk_g2s(s_w, mb.blk[pi], F16_BLOCK_FLOATS * 4, bar_w);
+    }
+    if (stid == 0 && t0 < n_tiles) prefetch(t0);
+    mbar_wait(bar_w, phase_w); phase_w ^= 1;
+    const bool three = mb.n_rgb[pi] == 3;
+    const int part = mb.out_part[pi];
 
     for (int tile = t0; tile < n_tiles; tile += stride) {
         const int row = tile * 128 + stid;
-        const int pr = min(row, n - 1);
+        const int sr = min(stid, n - 1 - tile * 128);               // rows past the list's end re-read its last row
         int surv;
         // ---- x = [e 19 | pe 27 | 0 0] -> X_hi / X_lo panels (row = stid): six 16-byte chunks of 8 halves each
+        mbar_wait(bar_full, phase_full); phase_full ^= 1;            // the tile's rows have landed in the staging buffer
         {
             float x[48];
-            const float4* e4 = reinterpret_cast<const float4*>(el + (size_t)pr * NVR_EMB_STRIDE);
+            const float4* e4 = reinterpret_cast<const float4*>(stage + (size_t)sr * NVR_EMB_STRIDE * 4);
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
-                const float4 t = __ldg(e4 + q);
+                const float4 t = e4[q];
                 x[q * 4] = t.x; x[q * 4 + 1] = t.y; x[q * 4 + 2] = t.z; x[q * 4 + 3] = t.w;   // x[19] is overwritten below
             }
-            const PairRec rec = pl[pr];
-            surv = rec.surv;
-            const float v[3] = {rec.vx, rec.vy, rec.vz};
+            const float4* r4 = reinterpret_cast<const float4*>(stage + F16_STAGE_E_BYTES + (size_t)sr * 32);
+            const float4 ra = r4[0], rb = r4[1];                     // PairRec: x y z vx | vy vz surv pad
+            surv = __float_as_int(rb.z);
+            const float v[3] = {ra.w, rb.x, rb.y};
             posenc27_doubling(v, x + 19);                           // part_base_network.py:54
             x[46] = 0.0f; x[47] = 0.0f;
 #pragma unroll
@@ -295,6 +325,7 @@ k_mlp_f16(const MlpBatch mb_param, float4* __restrict__ raws, int out_stride) {
         // ---- GEMM 0: h_pre = W0 e (accumulator in the H columns), and the x half of GEMM 2 queued right behind it into D:
         //      it needs nothing from the first epilogue and runs under it (covered by GEMM 2's commit, not by this one)
         if (stid == 0) {
+            if (tile + stride < n_tiles) prefetch(tile + stride);    // every thread of the slot has read its staged row (barrier above)
             tc_fence_after();
             gemm3h_ss<F16_K0, F16_K0>(tbase + F16_COL_H, s_xhi, s_xlo, s_p0, idesc, true);
             umma_commit(bar_a);
