@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 8
+#define NVR_ABI_VERSION 9
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -240,27 +240,42 @@ int nvr_prepare_inference(NvrHandle h, int32_t enable, void* stream);
  * must stay untouched between nvr_train_forward and the matching nvr_train_backward: it holds the
  * survivor / pair lists and embeddings the backward needs.
  *
- * Outputs besides raw (n,4) / occ (n): per SURVIVOR SLOT s < n_survivors (order = compaction order, not
- * sample order; sample_of_slot (n) maps a slot back to its sample index):
- *   x0 (n,5,3)   big-pose point before the residual (= ret['tpts'] rows s*5+p; zeros where the part is unflagged)
+ * Outputs besides raw (n,4) / occ (n): per SURVIVOR, in ascending sample order -- the order of the reference's nonzero()
+ * (inb_part_network_multiassign.py:137), rows r < n_survivors (later rows are zero):
+ *   x0 (n,5,3)   big-pose point before the residual (= ret['tpts'] rows r*5+p; zeros where the part is unflagged)
  *   resd (n,5,3) deformer residual (= ret['resd']; zeros where unflagged)
  *   tocc (n,5)   per-part occupancy (= ret['tocc']; zeros where unflagged)
+ * rank_of_slot (n) int32 receives the survivor-slot -> row map the backward needs (opaque to the caller).
  * The survivor count is read with nvr_read_counters after the call. */
 int nvr_train_forward(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw, float* occ,
-                      float* x0, float* resd, float* tocc, int32_t* sample_of_slot,
+                      float* x0, float* resd, float* tocc, int32_t* rank_of_slot,
                       void* workspace, size_t ws_bytes, void* stream);
 
 /* Bytes of extra scratch nvr_train_backward needs for a forward of n points. */
 size_t nvr_train_scratch_bytes(NvrHandle h, int64_t n);
 
 /* Backward of nvr_train_forward.  d_raw (n,4): gradient of the scattered raw (add the gradient of `occ` into
- * its 4th column: it is the same number).  d_resd (n,5,3) and d_tocc (n,5), slot order, may be NULL.
- * `x0` is the forward's x0 output.  `grads` has the layout of NvrParams but every pointer is the gradient
+ * its 4th column: it is the same number).  d_resd (n_survivors,5,3) and d_tocc (n_survivors,5), the forward's row order, may
+ * be NULL.  `x0` and `rank_of_slot` are the forward's outputs.  `grads` has the layout of NvrParams but every pointer is the gradient
  * buffer of that tensor (same shape, fp32, ACCUMULATED into; NULL = not wanted); non-pointer fields are ignored.
  * Gradient flow is the reference's: tables, MLPs, latent row, deformer; none through KNN / LBS / view dirs. */
 int nvr_train_backward(NvrHandle h, const float* d_raw, const float* d_resd, const float* d_tocc, const float* x0,
-                       int64_t n, const NvrParams* grads, void* workspace, size_t ws_bytes,
+                       const int32_t* rank_of_slot, int64_t n, const NvrParams* grads, void* workspace, size_t ws_bytes,
                        void* scratch, size_t scratch_bytes, void* stream);
+
+/* Training-time sampling along the rays (Renderer.get_wsampling_points, inb_renderer.py:15-31) in one launch:
+ * z = near (1 - t) + far t, t = linspace(0, 1, S); with `u` (n_rays, S) -- the reference's torch.rand draw, NULL when
+ * cfg.perturb == 0 -- the stratified jitter between the midpoints (:20-27); wpts = ray_o + ray_d z, viewdir = ray_d.
+ * Outputs z_vals (n_rays,S), wpts / viewdir (n_rays*S,3); same operation order as the reference's elementwise ops. */
+int nvr_train_sample(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_, const float* u,
+                     int64_t n_rays, int32_t n_samples, float* z_vals, float* wpts, float* viewdir, void* stream);
+
+/* Distortion regulariser (inb_renderer.py:96-103): loss[r] = sum_ij w_i w_j |m_i - m_j| with the interval midpoints
+ * m_k = (z_k + z_{k+1}) / 2, and its backward d_weights[r,i] = 2 d_loss[r] sum_j w_j |m_i - m_j| (z_vals are constants). */
+int nvr_distortion_forward(NvrHandle h, const float* weights, const float* z_vals, int64_t n_rays, int32_t n_samples,
+                           float* loss, void* stream);
+int nvr_distortion_backward(NvrHandle h, const float* weights, const float* z_vals, const float* d_loss, int64_t n_rays,
+                            int32_t n_samples, float* d_weights, void* stream);
 
 /* Backward of nvr_deformer_residual (Network.resd on explicit points, used by the pair regulariser):
  * tpts (n,3), d_resd (n,3) -> accumulates into grads->deformer_grid / deformer_mlp. */

@@ -44,6 +44,8 @@ struct NvrEngine {
     size_t presum_off[NVR_PARTS + 1] = {0};
     bool presum_valid = false;
     int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
+    cudaStream_t part_stream[NVR_PARTS] = {nullptr};   // training backward: the five parts' chains run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join[NVR_PARTS] = {nullptr};
     long long launches = 0;
     long long last_points = 0;
     // multi-GPU frame assembly (nvr_frame.cuh): the local buffer [flags | slot 0 | slot 1] and the peers' mappings
@@ -146,6 +148,10 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
         delete h;
         return 5;
     }
+    for (int p = 0; p < NVR_PARTS; ++p)
+        if (cudaStreamCreateWithFlags(&h->part_stream[p], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join[p], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); delete h; return 5; }
+    if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); delete h; return 5; }
     *out = h;
     return 0;
 }
@@ -155,6 +161,8 @@ extern "C" int nvr_destroy(NvrHandle h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_dist); cudaFree(h->d_verts); cudaFree(h->d_cl_off); cudaFree(h->d_perm); cudaFree(h->d_part_mlp); cudaFree(h->d_part_grid); cudaFree(h->d_mlp_blocks); cudaFree(h->d_presum); cudaFree(h->d_counters_snapshot);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (int p = 0; p < NVR_PARTS; ++p) { if (h->part_stream[p]) cudaStreamDestroy(h->part_stream[p]); if (h->ev_join[p]) cudaEventDestroy(h->ev_join[p]); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->h_pass_counters) cudaFreeHost(h->h_pass_counters);
     frame_release(h);
     delete h;
@@ -372,7 +380,8 @@ static const float4* far_raws(const NvrEngine* h, const Workspace& w, bool on) {
 }
 static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const float* ray_d, const float* near_,
                     const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
-                    float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr, bool full_tables = false) {
+                    float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr, bool full_tables = false,
+                    int* rank_of_slot = nullptr) {
     const int sm = h->sm_count;
     const bool dense_a1 = (h->cfg.tune & NVR_TUNE_DENSE_A1) && !dbg && !out_x0;   // measurement variant (a = 1)
     NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
@@ -380,6 +389,10 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     NVR_CHECK(h, cudaMemsetAsync(w.surv_of_sample, 0xFF, (size_t)n * sizeof(int), st));   // -1 = culled; k_cull fills in the survivors
     k_cull<<<grid_for(n, 256 * CULL_T, sm * 8), 256, 0, st>>>(h->fdev, pts, ray_d, near_, far_, n, n_samples, h->cfg.smpl_thresh,
                                                       w.counters, w.surv_of_sample, w.surv, dense_a1 ? 1 : 0); }
+    if (rank_of_slot) {      // training: survivors' positions in ascending sample order (the order the reference returns them in)
+        k_rank_slots<<<1, 1024, 0, st>>>(w.surv_of_sample, n, rank_of_slot);
+        h->launches++;
+    }
     // neighbour records alias the embedding buffer: they are consumed by k_warp before k_embed writes it
     KnnRec* recs = (KnnRec*)w.emb;
     const int far_slot = far_collapse(h, dbg, out_x0) ? (int)w.cap - 1 : -1;
@@ -393,9 +406,9 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     { StageTimer t(h, st, NVR_STAGE_WARP);
     const dim3 wg(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS);
     if (!(h->cfg.tune & NVR_TUNE_WARP_OCC4))    // <= 64 registers: 8 CTAs (32 warps) per SM instead of 4
-        k_warp<8><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd);
+        k_warp<8><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd, rank_of_slot);
     else
-        k_warp<1><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd); }
+        k_warp<1><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd, rank_of_slot); }
     const bool tc = h->cfg.mlp_mode >= 1;
     if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
         StageTimer t(h, st, NVR_STAGE_MLP);
@@ -771,21 +784,21 @@ extern "C" int nvr_prepare_inference(NvrHandle h, int32_t enable, void* stream_)
 }
 
 // ---- training ----------------------------------------------------------------------------------
-__global__ void k_export_slots(const int* __restrict__ counters, const float4* __restrict__ surv, const float4* __restrict__ raws,
-                               float* __restrict__ tocc, int* __restrict__ sample_of_slot) {
+__global__ void k_export_slots(const int* __restrict__ counters, const float4* __restrict__ raws, const int* __restrict__ rank_of_slot,
+                               float* __restrict__ tocc) {
     const int n = counters[NVR_CTR_SURV];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        sample_of_slot[s] = __float_as_int(surv[s].w);
+        const long long row = rank_of_slot[s];
 #pragma unroll
-        for (int p = 0; p < NVR_PARTS; ++p) tocc[(long long)s * NVR_PARTS + p] = raws[(long long)s * NVR_PARTS + p].w;
+        for (int p = 0; p < NVR_PARTS; ++p) tocc[row * NVR_PARTS + p] = raws[(long long)s * NVR_PARTS + p].w;
     }
 }
 
 extern "C" int nvr_train_forward(NvrHandle h, const float* wpts, const float* viewdir, int64_t n, float* raw, float* occ,
-                                 float* x0, float* resd, float* tocc, int32_t* sample_of_slot, void* workspace, size_t ws_bytes,
+                                 float* x0, float* resd, float* tocc, int32_t* rank_of_slot, void* workspace, size_t ws_bytes,
                                  void* stream_) {
     if (int rc = ready(h, "nvr_train_forward")) return rc;
-    if (n < 0 || (n > 0 && (!wpts || !viewdir || !raw || !x0 || !resd || !tocc || !sample_of_slot)))
+    if (n < 0 || (n > 0 && (!wpts || !viewdir || !raw || !x0 || !resd || !tocc || !rank_of_slot)))
         return fail(h, "nvr_train_forward: null argument");
     Workspace w;
     if (!carve(workspace, ws_bytes, w) || w.pts < n) return fail(h, "nvr_train_forward: workspace must hold all points in one pass");
@@ -794,9 +807,9 @@ extern "C" int nvr_train_forward(NvrHandle h, const float* wpts, const float* vi
     NVR_CHECK(h, cudaMemsetAsync(x0, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
     NVR_CHECK(h, cudaMemsetAsync(resd, 0, (size_t)n * NVR_NUM_PARTS * 3 * sizeof(float), st));
     NVR_CHECK(h, cudaMemsetAsync(tocc, 0, (size_t)n * NVR_NUM_PARTS * sizeof(float), st));
-    if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, nullptr, x0, resd, true)) return rc;
+    if (int rc = run_pass(h, w, wpts, nullptr, nullptr, nullptr, n, 0, viewdir, 1, st, nullptr, x0, resd, true, rank_of_slot)) return rc;
     k_resolve_points<<<grid_for(n, 256, h->sm_count * 16), 256, 0, st>>>(w.surv_of_sample, w.raws, nullptr, n, (float4*)raw, occ);
-    k_export_slots<<<grid_for(n, 256, h->sm_count * 8), 256, 0, st>>>(w.counters, w.surv, w.raws, tocc, sample_of_slot);
+    k_export_slots<<<grid_for(n, 256, h->sm_count * 8), 256, 0, st>>>(w.counters, w.raws, rank_of_slot, tocc);
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 2;
     return snapshot_counters(h, w, st);
@@ -822,10 +835,10 @@ static DeformerGrad deformer_grad(const NvrParams* g) {
 }
 
 extern "C" int nvr_train_backward(NvrHandle h, const float* d_raw, const float* d_resd, const float* d_tocc, const float* x0,
-                                  int64_t n, const NvrParams* grads, void* workspace, size_t ws_bytes, void* scratch,
-                                  size_t scratch_bytes, void* stream_) {
+                                  const int32_t* rank_of_slot, int64_t n, const NvrParams* grads, void* workspace, size_t ws_bytes,
+                                  void* scratch, size_t scratch_bytes, void* stream_) {
     if (int rc = ready(h, "nvr_train_backward")) return rc;
-    if (n < 0 || !grads || (n > 0 && (!d_raw || !x0))) return fail(h, "nvr_train_backward: null argument");
+    if (n < 0 || !grads || (n > 0 && (!d_raw || !x0 || !rank_of_slot))) return fail(h, "nvr_train_backward: null argument");
     Workspace w;
     if (!carve(workspace, ws_bytes, w) || w.pts < n) return fail(h, "nvr_train_backward: not the forward's workspace");
     if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < train_scratch_bytes(w.cap))
@@ -843,9 +856,15 @@ extern "C" int nvr_train_backward(NvrHandle h, const float* d_raw, const float* 
     const int sm = h->sm_count;
     NVR_CHECK(h, cudaMemsetAsync(gcount, 0, 64, st));
     k_bwd_select<<<dim3(grid_for(n, 256, sm * 4), NVR_NUM_PARTS), 256, 0, st>>>(w.counters, w.pairs, (int)cap, w.surv, w.raws,
-                                                                              (const float4*)d_raw, d_tocc, glist, gcount);
-    k_bwd_resd_list<<<dim3(grid_for(n, 256, sm * 4), NVR_NUM_PARTS), 256, 0, st>>>(w.counters, w.pairs, (int)cap, x0, d_resd, wl_x0, wl_dr);
+                                                                              (const float4*)d_raw, d_tocc, rank_of_slot, glist, gcount);
+    k_bwd_resd_list<<<dim3(grid_for(n, 256, sm * 4), NVR_NUM_PARTS), 256, 0, st>>>(w.counters, w.pairs, (int)cap, x0, d_resd, rank_of_slot, wl_x0, wl_dr);
+    // the five parts' chains are independent (they only meet in atomic adds on the deformer's gradients) and, at training sizes,
+    // each kernel is a handful of CTAs: run them side by side on the engine's part streams instead of back to back
+    NVR_CHECK(h, cudaEventRecord(h->ev_fork, st));
+    cudaStream_t caller = st;
     for (int pt = 0; pt < NVR_NUM_PARTS; ++pt) {
+        st = h->part_stream[pt];
+        NVR_CHECK(h, cudaStreamWaitEvent(st, h->ev_fork, 0));
         const NvrPart& gp = grads->part[pt];
         const GradRec* gl = glist + (size_t)pt * cap;
         const PairRec* pl = w.pairs + (size_t)pt * cap;
@@ -860,10 +879,52 @@ extern "C" int nvr_train_backward(NvrHandle h, const float* d_raw, const float* 
         k_deformer_bwd<<<grid_for(n, BT, sm), BTHREADS, DB_SMEM_BYTES, st>>>(
             h->fdev, h->def_grid, h->def_mlp, deformer_grad(grads), GridGrad{(float*)grads->deformer_grid.dense, (float*)grads->deformer_grid.hash},
             wl_x0 + (size_t)pt * cap * 3, wl_dr + (size_t)pt * cap * 3, w.counters + NVR_CTR_PAIR + pt, 0);
+        NVR_CHECK(h, cudaEventRecord(h->ev_join[pt], st));
+        NVR_CHECK(h, cudaStreamWaitEvent(caller, h->ev_join[pt], 0));
     }
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 2 + 4 * NVR_NUM_PARTS;
     return 0;
+}
+
+// ---- training-time sampling and the distortion regulariser (inb_renderer.py:15-31, 96-103) ------------------------------
+extern "C" int nvr_train_sample(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
+                                const float* u, int64_t n_rays, int32_t n_samples, float* z_vals, float* wpts, float* viewdir,
+                                void* stream_) {
+    if (!h) return 1;
+    if (n_rays < 0 || n_samples < 1 || (n_rays > 0 && (!ray_o || !ray_d || !near_ || !far_ || !z_vals || !wpts || !viewdir)))
+        return fail(h, "nvr_train_sample: bad argument");
+    if (n_rays == 0) return 0;
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    k_train_sample<<<grid_for(n_rays * n_samples, 256, h->sm_count * 8), 256, 0, (cudaStream_t)stream_>>>(ray_o, ray_d, near_, far_, u, n_rays, n_samples,
+                                                                                                    z_vals, wpts, viewdir);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+static int distortion_launch(NvrHandle h, const float* weights, const float* z_vals, const float* d_loss, int64_t n_rays, int32_t S,
+                             float* loss, float* d_weights, void* stream_) {
+    if (n_rays == 0) return 0;
+    if (S > 4096) return fail(h, "nvr_distortion: more than 4096 samples per ray");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    k_distortion<<<grid_for(n_rays, 8, h->sm_count * 8), 256, 8 * 2 * S * sizeof(float), (cudaStream_t)stream_>>>(weights, z_vals, d_loss, n_rays, S, loss, d_weights);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+extern "C" int nvr_distortion_forward(NvrHandle h, const float* weights, const float* z_vals, int64_t n_rays, int32_t n_samples,
+                                      float* loss, void* stream_) {
+    if (!h) return 1;
+    if (n_rays < 0 || n_samples < 1 || (n_rays > 0 && (!weights || !z_vals || !loss))) return fail(h, "nvr_distortion_forward: bad argument");
+    return distortion_launch(h, weights, z_vals, nullptr, n_rays, n_samples, loss, nullptr, stream_);
+}
+extern "C" int nvr_distortion_backward(NvrHandle h, const float* weights, const float* z_vals, const float* d_loss, int64_t n_rays,
+                                       int32_t n_samples, float* d_weights, void* stream_) {
+    if (!h) return 1;
+    if (n_rays < 0 || n_samples < 1 || (n_rays > 0 && (!weights || !z_vals || !d_loss || !d_weights)))
+        return fail(h, "nvr_distortion_backward: bad argument");
+    return distortion_launch(h, weights, z_vals, d_loss, n_rays, n_samples, nullptr, d_weights, stream_);
 }
 
 extern "C" int nvr_deformer_backward(NvrHandle h, const float* tpts, const float* d_resd, int64_t n, const NvrParams* grads, void* stream_) {

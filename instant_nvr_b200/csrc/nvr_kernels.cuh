@@ -463,6 +463,41 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
     }
 }
 
+// Training: rank_of_slot[slot] = position of the survivor in ASCENDING SAMPLE ORDER (the order of the reference's
+// nonzero(), inb_part_network_multiassign.py:137), from the sample -> slot map.  One CTA: every thread counts the survivors of
+// its contiguous chunk of samples, a block scan turns the counts into offsets, a second sweep hands out the ranks.
+__global__ void __launch_bounds__(1024)
+k_rank_slots(const int* __restrict__ surv_of_sample, long long n, int* __restrict__ rank_of_slot) {
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long chunk = (n + blockDim.x - 1) / blockDim.x, lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    int cnt = 0;
+    for (long long i = lo; i < hi; ++i) cnt += surv_of_sample[i] >= 0;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += up;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += up;
+        }
+        s_warp[lane] = v;
+    }
+    __syncthreads();
+    int rank = incl - cnt + (wid ? s_warp[wid - 1] : 0);
+    for (long long i = lo; i < hi; ++i) {
+        const int slot = surv_of_sample[i];
+        if (slot >= 0) rank_of_slot[slot] = rank++;
+    }
+}
+
 // -----------------------------------------------------------------------------------------
 // knn: survivors -> flagged (sample, part) neighbour records
 // -----------------------------------------------------------------------------------------
@@ -621,8 +656,10 @@ template <int MINB>
 __global__ void __launch_bounds__(WARP_THREADS, MINB)
 k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs, int dir_div,
        const int* __restrict__ counters, const float4* __restrict__ surv, const KnnRec* __restrict__ recs,
-       PairRec* __restrict__ pairs, int cap, float* __restrict__ dbg, float* __restrict__ out_x0, float* __restrict__ out_resd) {
-    // out_x0 / out_resd (training): (slots, 5, 3) big-pose point and residual of every flagged (survivor, part)
+       PairRec* __restrict__ pairs, int cap, float* __restrict__ dbg, float* __restrict__ out_x0, float* __restrict__ out_resd,
+       const int* __restrict__ out_rank) {
+    // out_x0 / out_resd (training): (survivors, 5, 3) big-pose point and residual of every flagged (survivor, part), row =
+    // out_rank[slot] (the survivor's position in ascending sample order, k_rank_slots) or the slot itself when out_rank is null
     __shared__ __align__(16) float sm[WARP_SMEM_FLOATS];
     const int part = blockIdx.y;
     const int n = counters[NVR_CTR_PAIR + part];
@@ -648,7 +685,7 @@ k_warp(FrameDev fr, GridDev dg, DeformerMlp dm_g, const float* __restrict__ dirs
         out.surv = rec.surv; out._pad = 0;
         pairs[(long long)part * cap + i] = out;
         if (out_x0) {
-            const long long o3 = ((long long)rec.surv * NVR_PARTS + part) * 3;
+            const long long o3 = ((long long)(out_rank ? out_rank[rec.surv] : rec.surv) * NVR_PARTS + part) * 3;
 #pragma unroll
             for (int a = 0; a < 3; ++a) { out_x0[o3 + a] = x0[a]; out_resd[o3 + a] = r[a]; }
         }

@@ -97,12 +97,12 @@ __device__ __forceinline__ float softplus_grad_from_out(float sp) { return 1.0f 
 // ---------------------------------------------------------------------------------------------------
 // which pairs receive a gradient                                   inb_part_network_multiassign.py:253-255
 // ---------------------------------------------------------------------------------------------------
-// d_raw: (n_samples, 4) gradient of the scattered raw; d_tocc: optional (cap, 5) gradient of every pair's
-// occupancy in survivor-slot order.  blockIdx.y = part.
+// d_raw: (n_samples, 4) gradient of the scattered raw; d_tocc: optional (survivors, 5) gradient of every pair's
+// occupancy, row rank_of_slot[slot] (ascending sample order; the slot itself when rank_of_slot is null).  blockIdx.y = part.
 __global__ void __launch_bounds__(256)
 k_bwd_select(const int* __restrict__ counters, const PairRec* __restrict__ pairs, int cap, const float4* __restrict__ surv,
              const float4* __restrict__ raws, const float4* __restrict__ d_raw, const float* __restrict__ d_tocc,
-             GradRec* __restrict__ glist, int* __restrict__ gcount) {
+             const int* __restrict__ rank_of_slot, GradRec* __restrict__ glist, int* __restrict__ gcount) {
     const int part = blockIdx.y;
     const int n = counters[NVR_CTR_PAIR + part];
     const int lane = threadIdx.x & 31;
@@ -125,7 +125,7 @@ k_bwd_select(const int* __restrict__ counters, const PairRec* __restrict__ pairs
                 const float4 dr = d_raw[__float_as_int(surv[s].w)];
                 d[0] = dr.x; d[1] = dr.y; d[2] = dr.z; d[3] = dr.w;
             }
-            if (d_tocc) d[3] += d_tocc[(long long)s * NVR_PARTS + part];
+            if (d_tocc) d[3] += d_tocc[(long long)(rank_of_slot ? rank_of_slot[s] : s) * NVR_PARTS + part];
             has = d[0] != 0.f || d[1] != 0.f || d[2] != 0.f || d[3] != 0.f;
             g.pair = i; g.surv = s; g.d[0] = d[0]; g.d[1] = d[1]; g.d[2] = d[2]; g.d[3] = d[3]; g._pad[0] = g._pad[1] = 0;
         }
@@ -509,12 +509,12 @@ k_deformer_bwd(FrameDev fr, GridDev dg, DeformerMlp dm, DeformerGrad dgr, GridGr
 // (their d_r is zero) so the list is simply the part's pair list.  blockIdx.y = part.
 __global__ void k_bwd_resd_list(const int* __restrict__ counters, const PairRec* __restrict__ pairs, int cap,
                                 const float* __restrict__ x0_slots, const float* __restrict__ d_resd_slots,
-                                float* __restrict__ wl_x0, float* __restrict__ wl_dr) {
+                                const int* __restrict__ rank_of_slot, float* __restrict__ wl_x0, float* __restrict__ wl_dr) {
     const int part = blockIdx.y;
     const int n = counters[NVR_CTR_PAIR + part];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int s = pairs[(long long)part * cap + i].surv;
-        const long long src = ((long long)s * NVR_PARTS + part) * 3, dst = ((long long)part * cap + i) * 3;
+        const long long src = ((long long)(rank_of_slot ? rank_of_slot[s] : s) * NVR_PARTS + part) * 3, dst = ((long long)part * cap + i) * 3;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             wl_x0[dst + a] = x0_slots[src + a];
@@ -576,5 +576,73 @@ __global__ void k_composite_bwd(const float4* __restrict__ raw, long long n_rays
             d_raw[ray * S + k] = make_float4(w * gr, w * gg, w * gb, Ti * (dw - Q));
             Q = r.w * dw + (1.0f - r.w) * Q;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training-time sampling along the rays                                         inb_renderer.py:15-31
+// ---------------------------------------------------------------------------------------------------
+// z = near (1 - t) + far t (t = linspace(0, 1, S)); with `u` (the reference's torch.rand draw, (R,S)) the stratified jitter
+// z' = lower + (upper - lower) u between the midpoints; wpts = o + d z', viewdir = d.  Separate multiplies and adds like the
+// reference's elementwise torch ops (no FMA contraction): z_vals feeds the distortion regulariser bit for bit.
+__global__ void k_train_sample(const float* __restrict__ ray_o, const float* __restrict__ ray_d, const float* __restrict__ near_,
+                               const float* __restrict__ far_, const float* __restrict__ u, long long n_rays, int S,
+                               float* __restrict__ z_vals, float* __restrict__ wpts, float* __restrict__ viewdir) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rays * S; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / S;
+        const int k = (int)(i - r * S);
+        const float nr = near_[r], fa = far_[r];
+        auto zk = [&](int kk) {
+            const float t = nvr_linspace01(kk, S);
+            return __fadd_rn(__fmul_rn(nr, 1.0f - t), __fmul_rn(fa, t));                        // :18
+        };
+        float z = zk(k);
+        if (u) {                                                                               // :20-27
+            const float lower = k > 0 ? __fmul_rn(0.5f, __fadd_rn(z, zk(k - 1))) : z;
+            const float upper = k < S - 1 ? __fmul_rn(0.5f, __fadd_rn(zk(k + 1), z)) : z;
+            z = __fadd_rn(lower, __fmul_rn(upper - lower, u[i]));
+        }
+        z_vals[i] = z;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float d = ray_d[r * 3 + a];
+            wpts[i * 3 + a] = __fadd_rn(ray_o[r * 3 + a], __fmul_rn(d, z));                    // :29
+            viewdir[i * 3 + a] = d;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// distortion regulariser                                                        inb_renderer.py:96-103
+// ---------------------------------------------------------------------------------------------------
+// loss_r = sum_ij w_i w_j |m_i - m_j|, m_k = (z_k + z_{k+1}) / 2 (the last interval has zero length: m_{S-1} = z_{S-1}).
+// One warp per ray; backward: d w_i = 2 g_r sum_j w_j |m_i - m_j| (z carries no gradient: the sample depths are constants).
+__global__ void __launch_bounds__(256)
+k_distortion(const float* __restrict__ weights, const float* __restrict__ z_vals, const float* __restrict__ d_loss, long long n_rays,
+             int S, float* __restrict__ loss, float* __restrict__ d_weights) {
+    extern __shared__ float sm_d[];                               // [warps][2][S]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* sw = sm_d + (size_t)wid * 2 * S;
+    float* smid = sw + S;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rays; r += ((long long)gridDim.x * blockDim.x) >> 5) {
+        for (int k = lane; k < S; k += 32) {
+            const float z = z_vals[r * S + k], zn = z_vals[r * S + (k + 1 < S ? k + 1 : k)];
+            sw[k] = weights[r * S + k];
+            smid[k] = (z + zn) / 2;
+        }
+        __syncwarp();
+        float acc = 0.0f;
+        const float g = d_loss ? d_loss[r] : 0.0f;
+        for (int i = lane; i < S; i += 32) {
+            float row = 0.0f;
+            const float mi = smid[i];
+            for (int j = 0; j < S; ++j) row += sw[j] * fabsf(mi - smid[j]);
+            acc += sw[i] * row;
+            if (d_weights) d_weights[r * S + i] = 2.0f * g * row;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (loss && lane == 0) loss[r] = acc;
+        __syncwarp();
     }
 }

@@ -287,12 +287,12 @@ class Engine:
         dev, f32 = self.device, torch.float32
         st = {"raw": torch.empty(n, 4, dtype=f32, device=dev), "occ": torch.empty(n, dtype=f32, device=dev),
               "x0": torch.empty(n, 5, 3, dtype=f32, device=dev), "resd": torch.empty(n, 5, 3, dtype=f32, device=dev),
-              "tocc": torch.empty(n, 5, dtype=f32, device=dev), "sample_of_slot": torch.empty(n, dtype=torch.int32, device=dev),
+              "tocc": torch.empty(n, 5, dtype=f32, device=dev), "rank_of_slot": torch.empty(n, dtype=torch.int32, device=dev),
               "ws": torch.empty(int(self.lib.nvr_workspace_bytes(self._h, max(n, 64))), dtype=torch.uint8, device=dev),
               "n": n, "batch": batch}
         self._check(self.lib.nvr_train_forward(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, st["raw"].data_ptr(),
                                                st["occ"].data_ptr(), st["x0"].data_ptr(), st["resd"].data_ptr(),
-                                               st["tocc"].data_ptr(), st["sample_of_slot"].data_ptr(), st["ws"].data_ptr(),
+                                               st["tocc"].data_ptr(), st["rank_of_slot"].data_ptr(), st["ws"].data_ptr(),
                                                st["ws"].numel(), _stream_ptr(self.device)), "nvr_train_forward")
         st["n_surv"] = int(self.counters()["n_survivors"]) if n else 0      # one host sync (the reference has seven)
         return st
@@ -307,7 +307,8 @@ class Engine:
         d_resd = None if d_resd is None else _dev_f32(d_resd, self.device)      # converted ONCE: the pointers below are theirs
         d_tocc = None if d_tocc is None else _dev_f32(d_tocc, self.device)
         ptr = lambda t: 0 if t is None else t.data_ptr()
-        self._check(self.lib.nvr_train_backward(self._h, d_raw.data_ptr(), ptr(d_resd), ptr(d_tocc), st["x0"].data_ptr(), n,
+        self._check(self.lib.nvr_train_backward(self._h, d_raw.data_ptr(), ptr(d_resd), ptr(d_tocc), st["x0"].data_ptr(),
+                                                st["rank_of_slot"].data_ptr(), n,
                                                 C.byref(G), st["ws"].data_ptr(), st["ws"].numel(), scratch.data_ptr(),
                                                 scratch.numel(), _stream_ptr(self.device)), "nvr_train_backward")
 
@@ -318,6 +319,36 @@ class Engine:
         G = _params_struct(net, grads)
         self._check(self.lib.nvr_deformer_backward(self._h, tpts.data_ptr(), d_resd.data_ptr(), tpts.shape[0], C.byref(G),
                                                    _stream_ptr(self.device)), "nvr_deformer_backward")
+
+    def train_sample(self, ray_o, ray_d, near, far, n_samples: int, u: Optional[torch.Tensor]):
+        """Renderer.get_wsampling_points in one launch: rays (R,3),(R,3),(R,),(R,) [+ the jitter draw u (R,S)] ->
+        z_vals (R,S), wpts (R*S,3), viewdir (R*S,3)."""
+        dev = self.device
+        ray_o, ray_d, near, far = (_dev_f32(t, dev) for t in (ray_o, ray_d, near, far))
+        u = None if u is None else _dev_f32(u, dev)
+        R = ray_o.shape[0]
+        z = torch.empty(R, n_samples, dtype=torch.float32, device=dev)
+        wpts = torch.empty(R * n_samples, 3, dtype=torch.float32, device=dev)
+        vd = torch.empty(R * n_samples, 3, dtype=torch.float32, device=dev)
+        self._check(self.lib.nvr_train_sample(self._h, ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(), far.data_ptr(),
+                                              None if u is None else u.data_ptr(), R, int(n_samples), z.data_ptr(), wpts.data_ptr(),
+                                              vd.data_ptr(), _stream_ptr(dev)), "nvr_train_sample")
+        return z, wpts, vd
+
+    def distortion_forward(self, weights: torch.Tensor, z_vals: torch.Tensor) -> torch.Tensor:
+        R, S = weights.shape
+        loss = torch.empty(R, dtype=torch.float32, device=self.device)
+        self._check(self.lib.nvr_distortion_forward(self._h, weights.data_ptr(), z_vals.data_ptr(), R, S, loss.data_ptr(),
+                                                    _stream_ptr(self.device)), "nvr_distortion_forward")
+        return loss
+
+    def distortion_backward(self, weights: torch.Tensor, z_vals: torch.Tensor, d_loss: torch.Tensor) -> torch.Tensor:
+        R, S = weights.shape
+        d_w = torch.empty(R, S, dtype=torch.float32, device=self.device)
+        d_loss = _dev_f32(d_loss, self.device)
+        self._check(self.lib.nvr_distortion_backward(self._h, weights.data_ptr(), z_vals.data_ptr(), d_loss.data_ptr(), R, S,
+                                                     d_w.data_ptr(), _stream_ptr(self.device)), "nvr_distortion_backward")
+        return d_w
 
     def composite_forward(self, raw: torch.Tensor):
         raw = _dev_f32(raw, self.device)

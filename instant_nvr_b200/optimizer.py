@@ -63,17 +63,19 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        by_hyper: Dict[tuple, List[cabi.NvrAdamTensor]] = {}
-        touched: List[torch.Tensor] = []
+        # one NvrAdamTensor per parameter with a gradient, grouped by (beta1, beta2, eps).  The ctypes arrays are cached between
+        # steps and only re-built when a pointer moved (a new gradient buffer, a re-loaded state): per step the host then just
+        # bumps `step` / `lr` in place instead of constructing 67 structs
+        entries, touched = [], []
         device = None
         for group in self.param_groups:
             if group.get("amsgrad") or group.get("maximize") or group.get("decoupled_weight_decay"):
                 raise RuntimeError("FusedAdam implements plain Adam only (amsgrad / maximize / AdamW are not on the reference's path)")
-            beta1, beta2 = group["betas"]
+            hyper = (float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]))
             for p in group["params"]:
-                if p.grad is None:
-                    continue
                 g = p.grad
+                if g is None:
+                    continue
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("FusedAdam: parameters must be contiguous fp32 CUDA tensors (there is no CPU path)")
                 if g.is_sparse or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device:
@@ -88,18 +90,34 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
-                t = cabi.NvrAdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                                       p.numel(), int(st["step"].item()), float(group["lr"]), float(group["weight_decay"]))
-                by_hyper.setdefault((float(beta1), float(beta2), float(group["eps"])), []).append(t)
+                entries.append((hyper, p, g, st, float(group["lr"]), float(group["weight_decay"])))
                 touched += [p, st["exp_avg"], st["exp_avg_sq"]] + ([g] if self.zero_grad_in_step else [])
         if device is None:
             return loss
+        key = tuple((e[0], e[1].data_ptr(), e[2].data_ptr(), e[3]["exp_avg"].data_ptr(), e[3]["exp_avg_sq"].data_ptr(), e[1].numel())
+                    for e in entries)
+        cache = getattr(self, "_pack", None)
+        if cache is None or cache["key"] != key:
+            by_hyper: Dict[tuple, List[int]] = {}
+            for i, e in enumerate(entries):
+                by_hyper.setdefault(e[0], []).append(i)
+            arrays = []
+            for hyper, idxs in by_hyper.items():
+                arr = (cabi.NvrAdamTensor * len(idxs))()
+                for j, i in enumerate(idxs):
+                    _, p, g, st, _, _ = entries[i]
+                    arr[j].param, arr[j].grad = p.data_ptr(), g.data_ptr()
+                    arr[j].exp_avg, arr[j].exp_avg_sq, arr[j].numel = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
+                arrays.append((hyper, idxs, arr))
+            cache = self._pack = {"key": key, "arrays": arrays}
         lib, h = aux_handle(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         with torch.cuda.device(device):
-            for (beta1, beta2, eps), ts in by_hyper.items():
-                arr = (cabi.NvrAdamTensor * len(ts))(*ts)
-                check(lib, h, lib.nvr_adam_step(h, arr, len(ts), beta1, beta2, eps, int(self.zero_grad_in_step), stream),
+            for (beta1, beta2, eps), idxs, arr in cache["arrays"]:
+                for j, i in enumerate(idxs):
+                    _, _, _, st, lr, wd = entries[i]
+                    arr[j].step, arr[j].lr, arr[j].weight_decay = int(st["step"]), lr, wd
+                check(lib, h, lib.nvr_adam_step(h, arr, len(idxs), beta1, beta2, eps, int(self.zero_grad_in_step), stream),
                       "nvr_adam_step")
         # the library wrote through raw pointers: tell autograd / anything keyed on tensor versions (the engine's
         # pre-summed inference tables) that these tensors changed in place, as torch.optim.Adam's in-place ops would

@@ -34,8 +34,8 @@ def zero_grads(params: Dict[str, torch.Tensor], names: List[str]) -> Dict[str, t
 
 
 class _NetworkTrainFn(torch.autograd.Function):
-    """raw (N,4), occ (N,1), resd (Ns,5,3), tocc (Ns,5) [differentiable]; x0 (Ns,5,3), sample_of_slot (Ns) [constants].
-    Slot order (compaction order) on this level; the caller re-orders to the reference's sample order."""
+    """raw (N,4), occ (N,1), resd (Ns,5,3), tocc (Ns,5) [differentiable]; x0 (Ns,5,3) [constant].  Survivor rows come out of
+    the library in the reference's order already (ascending sample index, nvr_train_forward)."""
 
     @staticmethod
     def forward(ctx, net, batch, wpts, viewdir, *params):
@@ -44,28 +44,22 @@ class _NetworkTrainFn(torch.autograd.Function):
         ctx.net, ctx.state = net, state
         ctx.names = [n for n, _ in trainable(net)]
         ns = state["n_surv"]
-        outs = (state["raw"], state["occ"][:, None], state["resd"][:ns], state["tocc"][:ns], state["x0"][:ns],
-                state["sample_of_slot"][:ns])
-        ctx.mark_non_differentiable(outs[4], outs[5])
+        outs = (state["raw"], state["occ"][:, None], state["resd"][:ns], state["tocc"][:ns], state["x0"][:ns])
+        ctx.mark_non_differentiable(outs[4])
         return outs
 
     @staticmethod
-    def backward(ctx, d_raw, d_occ, d_resd, d_tocc, _dx0, _dsos):
+    def backward(ctx, d_raw, d_occ, d_resd, d_tocc, _dx0):
         net, state = ctx.net, ctx.state
         eng = net.engine()
-        n, ns = state["raw"].shape[0], state["n_surv"]
-        g_raw = torch.zeros(n, 4, dtype=torch.float32, device=state["raw"].device) if d_raw is None else d_raw.contiguous().clone()
+        n = state["raw"].shape[0]
+        g_raw = torch.zeros(n, 4, dtype=torch.float32, device=state["raw"].device) if d_raw is None else d_raw.contiguous()
         if d_occ is not None:
+            g_raw = g_raw.clone() if d_raw is not None else g_raw
             g_raw[:, 3] += d_occ[:, 0]                       # 'occ' is the 4th column of the fused raw (:254-255)
-
-        def slots(g, tail):
-            if g is None:
-                return None
-            full = torch.zeros((n,) + tail, dtype=torch.float32, device=g.device)
-            full[:ns] = g
-            return full
         grads = zero_grads(dict(trainable(net)), ctx.names)
-        eng.train_backward(state, g_raw, slots(d_resd, (5, 3)), slots(d_tocc, (5,)), net, grads)
+        eng.train_backward(state, g_raw, None if d_resd is None else d_resd.contiguous(),
+                           None if d_tocc is None else d_tocc.contiguous(), net, grads)
         ctx.state = None
         return (None, None, None, None) + tuple(grads[name] for name in ctx.names)
 
@@ -74,9 +68,7 @@ def network_train_forward(net, wpts: torch.Tensor, viewdir: torch.Tensor, batch:
     """``Network.forward`` with ``self.training``: {'raw' (1,N,4), 'occ' (1,N,1), 'resd' (1,N',5,3),
     'tpts' (1,5N',3), 'tocc' (1,5N',1)} with survivors in the reference's order (ascending sample index)."""
     params = [p for _, p in trainable(net)]
-    raw, occ, resd, tocc, x0, sos = _NetworkTrainFn.apply(net, batch, wpts, viewdir, *params)
-    order = torch.argsort(sos.long())                        # compaction order -> nonzero() order (:137)
-    resd, tocc, x0 = resd[order], tocc[order], x0[order]
+    raw, occ, resd, tocc, x0 = _NetworkTrainFn.apply(net, batch, wpts, viewdir, *params)
     return {"raw": raw[None], "occ": occ[None], "resd": resd[None], "tpts": x0.reshape(1, -1, 3),
             "tocc": tocc.reshape(1, -1, 1)}
 
@@ -129,6 +121,22 @@ def composite(eng, raw: torch.Tensor):
     return _CompositeFn.apply(eng, raw)
 
 
+class _DistortionFn(torch.autograd.Function):
+    """reg_distortion_loss (inb_renderer.py:96-103): weights (R,S) [differentiable], z_vals (R,S) [constant] -> loss (R)."""
+
+    @staticmethod
+    def forward(ctx, eng, weights, z_vals):
+        weights, z_vals = weights.contiguous(), z_vals.contiguous()
+        ctx.eng = eng
+        ctx.save_for_backward(weights, z_vals)
+        return eng.distortion_forward(weights, z_vals)
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        weights, z_vals = ctx.saved_tensors
+        return None, ctx.eng.distortion_backward(weights, z_vals, d_loss.contiguous()), None
+
+
 def render_train(renderer, batch: Dict, epoch: int = -1) -> Dict[str, torch.Tensor]:
     """``Renderer.render`` with ``net.training`` (inb_renderer.py:53-239): stratified jitter, the network in
     training mode, compositing, pair and distortion regularisers.  Sampling-distance bookkeeping (linspace, the
@@ -142,21 +150,14 @@ def render_train(renderer, batch: Dict, epoch: int = -1) -> Dict[str, torch.Tens
     if n_batch != 1:
         raise ValueError("n_batch must be 1 (the reference asserts it, inb_part_network_multiassign.py:84)")
     S = cfg.N_samples
-    t_vals = torch.linspace(0.0, 1.0, steps=S, device=near.device, dtype=near.dtype)           # :17
-    z_vals = near[..., None] * (1.0 - t_vals) + far[..., None] * t_vals                         # :18
-    if cfg.perturb > 0.0:                                                                       # :20-27
-        mids = 0.5 * (z_vals[..., 1:] + z_vals[..., :-1])
-        upper = torch.cat([mids, z_vals[..., -1:]], -1)
-        lower = torch.cat([z_vals[..., :1], mids], -1)
-        z_vals = lower + (upper - lower) * torch.rand(z_vals.shape, device=upper.device, dtype=upper.dtype)
-    wpts = ray_o[:, :, None] + ray_d[:, :, None] * z_vals[..., None]                            # :29
-    viewdir = ray_d[:, :, None].expand(-1, -1, S, -1)
-    dists = z_vals[..., 1:] - z_vals[..., :-1]                                                  # :45-47 (unused downstream)
-    dists = torch.cat([dists, dists[..., -1:]], dim=2).reshape(-1)
-    ret = net(wpts.reshape(-1, 3).contiguous(), viewdir.reshape(-1, 3).contiguous(), dists, batch)
+    eng = net.engine()
+    # :15-31 in one launch; the stratified jitter keeps the reference's torch.rand draw (same generator, same shape)
+    u = torch.rand(n_batch, n_pixel, S, device=near.device, dtype=near.dtype) if cfg.perturb > 0.0 else None
+    z_vals, wpts, viewdir = eng.train_sample(ray_o[0], ray_d[0], near[0], far[0], S, None if u is None else u[0])
+    ret = net(wpts, viewdir, None, batch)                        # `dists` (:45-47) is dead in the reference's networks
 
     raw = ret["raw"].reshape(n_pixel, S, 4)
-    weights, rgb_map, acc_map = composite(net.engine(), raw)                                    # :72
+    weights, rgb_map, acc_map = composite(eng, raw)                                             # :72
     if cfg.use_pair_reg:                                                                        # :78-94
         tocc = ret["tocc"].view(-1)
         reg_inds = ((tocc - 0.5).abs() < 0.02).nonzero(as_tuple=True)[0]
@@ -168,11 +169,7 @@ def render_train(renderer, batch: Dict, epoch: int = -1) -> Dict[str, torch.Tens
         else:
             ret["oresd"] = torch.zeros(1, 0, 3, device=raw.device)
     if cfg.use_reg_distortion:                                                                  # :96-103
-        ww = weights.reshape(n_pixel, S, 1) * weights.reshape(n_pixel, 1, S)
-        nxt = torch.cat([z_vals[0, :, 1:], z_vals[0, :, -1:]], dim=-1)
-        mid = (z_vals[0] + nxt) / 2
-        diff = torch.abs(mid.reshape(n_pixel, S, 1) - mid.reshape(n_pixel, 1, S))
-        ret["reg_distortion_loss"] = (ww * diff).sum(dim=-1).sum(dim=-1)[None]
+        ret["reg_distortion_loss"] = _DistortionFn.apply(eng, weights, z_vals)[None]
     ret.update({"rgb_map": rgb_map[None], "acc_map": acc_map[None], "raw": raw.reshape(1, -1, 4)})
     ret["resd"] = ret["resd"].reshape(n_batch, ret["tpts"].shape[1], 3)                         # :134-136: (1, 5N', 3) out of the renderer
     if cfg.use_freespace_loss:                                                                  # :118-121

@@ -363,3 +363,44 @@ def test_fused_adam_step_refreshes_inference_tables():
     after_full = eng_full.render_rays(o, d, n, f, 16, batch=gb)[0]
     assert (after_sum - after_full).abs().max() < 2e-4
     assert (after_sum - before).abs().max() > 1e-3
+
+
+def test_train_sample_and_distortion_match_reference_formulas(setup):
+    """nvr_train_sample / nvr_distortion_* against the reference's own torch statements (inb_renderer.py:15-31, 96-103) run
+    eagerly on the same device: z_vals / wpts bit for bit (same operation order), the regulariser and its gradient to fp32
+    summation-order rounding."""
+    from instant_nvr_b200.training import _DistortionFn
+    eng = setup["net"].engine()
+    gb = setup["gbatch"]
+    ray_o, ray_d, near, far = gb["ray_o"], gb["ray_d"], gb["near"], gb["far"]
+    R = ray_o.shape[1]
+    for S, perturb in ((24, True), (64, True), (64, False), (1, False), (2, True)):
+        u = torch.rand(1, R, S, device="cuda", generator=torch.Generator(device="cuda").manual_seed(S)) if perturb else None
+        t_vals = torch.linspace(0.0, 1.0, steps=S, device="cuda")
+        z_ref = near[..., None] * (1.0 - t_vals) + far[..., None] * t_vals
+        if perturb:
+            mids = 0.5 * (z_ref[..., 1:] + z_ref[..., :-1])
+            upper = torch.cat([mids, z_ref[..., -1:]], -1)
+            lower = torch.cat([z_ref[..., :1], mids], -1)
+            z_ref = lower + (upper - lower) * u
+        w_ref = ray_o[:, :, None] + ray_d[:, :, None] * z_ref[..., None]
+        z, wpts, vd = eng.train_sample(ray_o[0], ray_d[0], near[0], far[0], S, None if u is None else u[0])
+        assert torch.equal(z, z_ref[0]), (S, perturb, (z - z_ref[0]).abs().max().item())
+        assert torch.equal(wpts.view(R, S, 3), w_ref[0])
+        assert torch.equal(vd.view(R, S, 3), ray_d[0][:, None].expand(R, S, 3))
+    S = 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    z = torch.sort(torch.rand(R, S, device="cuda", generator=g) * 2 + 2, dim=-1).values
+    w = torch.rand(R, S, device="cuda", generator=g) * 0.1
+    wr = w.clone().requires_grad_(True)
+    ww = wr.reshape(R, S, 1) * wr.reshape(R, 1, S)
+    nxt = torch.cat([z[:, 1:], z[:, -1:]], dim=-1)
+    mid = (z + nxt) / 2
+    ref = (ww * torch.abs(mid.reshape(R, S, 1) - mid.reshape(R, 1, S))).sum(dim=-1).sum(dim=-1)
+    G = torch.randn(R, device="cuda", generator=g)
+    (ref * G).sum().backward()
+    wo = w.clone().requires_grad_(True)
+    ours = _DistortionFn.apply(eng, wo, z)
+    (ours * G).sum().backward()
+    assert (ours - ref).abs().max() <= 1e-5 * ref.abs().max()
+    assert (wo.grad - wr.grad).abs().max() <= 1e-5 * wr.grad.abs().max()
