@@ -35,7 +35,15 @@ DEFAULT_TUNE = 0
 
 def _params_struct(net, grads: Optional[Dict[str, torch.Tensor]] = None) -> "cabi.NvrParams":
     """NvrParams over the module tree.  With ``grads`` (parameter name -> gradient buffer) the pointer fields hold the
-    gradient buffers instead (0 where absent), which is what nvr_train_backward / nvr_deformer_backward take."""
+    gradient buffers instead (0 where absent), which is what nvr_train_backward / nvr_deformer_backward take.
+    A gradient descriptor is cached per flat gradient buffer (``grads["_base"]``, training.zero_grads): the allocator hands
+    the same block back step after step, so the ~1 ms walk over the module tree happens once."""
+    base = None if grads is None else grads.get("_base")
+    if base is not None:
+        cache = net.__dict__.setdefault("_grad_struct_cache", {})
+        hit = cache.get(base)
+        if hit is not None and hit[0] is getattr(net, "_trainable_cache", None):
+            return hit[1]
     names = {id(p): n for n, p in net.named_parameters()}
 
     def ptr(t):
@@ -67,6 +75,10 @@ def _params_struct(net, grads: Optional[Dict[str, torch.Tensor]] = None) -> "cab
     P.deformer_grid = grid(net.tpose_deformer.embedder)
     for k, idx in enumerate((0, 2, 4)):
         P.deformer_mlp[k] = lin(net.tpose_deformer.mlp[idx])
+    if base is not None:
+        if len(cache) > 8:
+            cache.clear()
+        cache[base] = (getattr(net, "_trainable_cache", None), P)
     return P
 
 
@@ -95,6 +107,7 @@ class Engine:
         self._h = h
         self._params_key = None
         self._params_keep = None
+        self._params_net = None
         self._frame_key = None
         self._frame_keep = None
         self._topo_src = None
@@ -131,9 +144,12 @@ class Engine:
 
     def bind_params(self, net) -> None:
         """``net``: instant_nvr_b200.network.Network (or any module with the same tree)."""
+        if self._params_key is not None and self._params_net is net:
+            return                                   # bound; Network._apply() / invalidate_params() un-binds
         tensors = [p for p in net.parameters()]
         key = tuple(p.data_ptr() for p in tensors)
         if key == self._params_key:
+            self._params_net = net
             return
         for name, p in net.named_parameters():
             if p.device != self.device:
@@ -143,7 +159,7 @@ class Engine:
                 raise RuntimeError(f"parameter {name} is not contiguous")
         P = _params_struct(net)
         self._check(self.lib.nvr_bind_params(self._h, C.byref(P)), "nvr_bind_params")
-        self._params_key, self._params_keep = key, tensors
+        self._params_key, self._params_keep, self._params_net = key, tensors, net
         self._tables_key = None
         self._net_tables = [t for part in net.tpose_human.part_networks for t in (part.embedder.dense, part.embedder.hash)]
 

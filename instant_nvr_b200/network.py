@@ -50,11 +50,13 @@ class Network(nn.Module):
             self._engine = None                      # the module moved to another GPU: a new handle on that device
         if self._engine is None:
             self._engine = Engine(self.cfg, device=dev if dev.type == "cuda" else None)
-        self._engine.bind_params(self)
+        if self._engine._params_key is None:         # bound until _apply() (.cuda() / .to() / ...) replaces the storages
+            self._engine.bind_params(self)
         return self._engine
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
+        self._trainable_cache = None                 # training.trainable(): parameters may have been replaced
         if getattr(self, "_engine", None) is not None:
             self._engine.invalidate_params()
         return out
