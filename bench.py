@@ -279,20 +279,28 @@ def gather_uniform_roofline(eng, net, peak):
             "(52.7 MB) stay cache resident, the 10 hashed levels (671 MB) do not; includes the (n,19) fp32 output write"}
 
 
-def mlp_tensor_report(prof, steps):
-    """Tensor-core work of k_mlp_tc in the profiled pass: 3 kind::tf32 MMAs per 128x64x8 block (3xTF32)."""
+def mlp_tensor_report(prof, steps, mode):
+    """Tensor-core work of the part-MLP kernel in the profiled steps.  mlp_mode 3 (k_mlp_f16): three kind::f16 MMAs
+    (M=128, N=64, K=16) per K-step of the fp16-split product; modes 1 / 2 (k_mlp_tc): three kind::tf32 MMAs (K=8)."""
     pairs = prof["pairs"]
-    ksteps = [(24 + 48 + 64 + 64) // 8, (24 + 48 + 64) // 8, (24 + 48 + 64 + 64) // 8, (24 + 48 + 64) // 8, (24 + 48 + 64) // 8]
-    flops = sum(p * 3 * k * 2 * 64 * 8 for p, k in zip(pairs, ksteps))
+    k_elems = [32 + 48 + 64 + 64, 32 + 48 + 64, 32 + 48 + 64 + 64, 32 + 48 + 64, 32 + 48 + 64] if mode == 3 else \
+        [24 + 48 + 64 + 64, 24 + 48 + 64, 24 + 48 + 64 + 64, 24 + 48 + 64, 24 + 48 + 64]
+    kk = 16 if mode == 3 else 8
+    mmas = sum(((p + 127) // 128) * 3 * (k // kk) for p, k in zip(pairs, k_elems))
+    flops = mmas * 2 * 128 * 64 * kk
     ms = prof["ms"]["mlp"]
-    # one tcgen05.mma of M=128, N=64, K=8 (tf32) occupies the tensor pipe for max(M,128) * N / 256 = 32 cycles
-    mma_cycles = sum(((p + 127) // 128) * 3 * k * 32 for p, k in zip(pairs, ksteps))
     n_sm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    pipe_ms = mma_cycles / n_sm / 1.965e9 * 1e3
-    return {"kernel": "k_mlp_tc", "tf32_flops": flops / steps, "ms": ms / steps, "achieved_tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0,
-            "tensor_pipe_busy_estimate": pipe_ms / ms if ms > 0 else 0.0,
-            "note": "tensor_pipe_busy_estimate = issued tcgen05.mma x 32 cycles / (SMs x 1.965 GHz x kernel time); the measured "
-                    "sm__pipe_tensor_cycles_active is in profiles/*ncu_full_summary.csv"}
+    # one tcgen05.mma of M=128, N=64 occupies the tensor pipe for max(M,128) * N / 256 = 32 cycles whatever the kind
+    pipe_ms = mmas * 32 / n_sm / 1.965e9 * 1e3
+    # MUFU floor: 2 MUFU (ex2 + lg2) per hidden activation, 16 lanes per clock and SM
+    acts = sum(p * (192 if i in (0, 2) else 128) for i, p in enumerate(pairs))
+    mufu_ms = acts * 2 / 16 / n_sm / 1.965e9 * 1e3
+    return {"kernel": "k_mlp_f16" if mode == 3 else "k_mlp_tc", "operands": "fp16-split (hi+lo), kind::f16" if mode == 3 else "3xTF32, kind::tf32",
+            "mma_flops_per_step": flops / steps, "ms": ms / steps, "achieved_tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0,
+            "tensor_pipe_busy_estimate": pipe_ms / ms if ms > 0 else 0.0, "mufu_floor_frac": mufu_ms / ms if ms > 0 else 0.0,
+            "note": "tensor_pipe_busy_estimate = issued tcgen05.mma x 32 cycles / (SMs x 1.965 GHz x kernel time); mufu_floor_frac = "
+                    "(2 MUFU per softplus x activations / 16 per clock per SM) / kernel time: the unit that bounds this kernel (ncu: "
+                    "MIO-throttle stalls on the ex2 / lg2 lines); the measured sm__pipe_tensor_cycles_active is in profiles/*ncu_full_summary.csv"}
 
 
 def train_step_report(net, gframe, frame, n_rays=1024, n_samples=64, steps=10):
@@ -755,7 +763,7 @@ def main():
             "roofline": roofline,
             "roofline_l1_insitu": roofline_l1,
             "roofline_alu": alu,
-            "mlp_tensor": mlp_tensor_report(prof, p_steps),
+            "mlp_tensor": mlp_tensor_report(prof, p_steps, eng.mlp_mode),
             "stage_ms_per_step": stage_ms, "stage_share": stage_share,
             "stage_note": f"per-launch CUDA events over {p_steps} extra steps with every launch serialised on one stream "
                           f"({ms_prof / p_steps:.3f} ms/step in that mode); the headline steps run without the events",

@@ -646,3 +646,15 @@ def test_inference_tables_match_full_tables(gpu):
     finally:
         with torch.no_grad():
             tab.mul_(2.0)
+
+
+def test_eval_render_returns_raw_and_occ_lazily(gpu):
+    """Renderer.render (eval) hands out the reference's `raw` / `occ` keys (inb_renderer.py:111-115) on first access."""
+    from instant_nvr_b200.renderer import Renderer
+    net = gpu["nets"][1.0]
+    eager = Renderer(net, return_raw=True).render(dict(gpu["gbatch"]))
+    lazy = Renderer(net).render(dict(gpu["gbatch"]))
+    assert set(lazy.keys()) == {"rgb_map", "acc_map"} and "raw" in lazy and "occ" in lazy and "nope" not in lazy
+    assert torch.equal(lazy["rgb_map"], eager["rgb_map"])
+    assert torch.equal(lazy["occ"], eager["occ"]) and torch.equal(lazy["raw"], eager["raw"])
+    assert set(lazy.keys()) == {"rgb_map", "acc_map", "raw", "occ"} and lazy["raw"].device.type == "cpu"
