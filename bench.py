@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--assemble", choices=["peer", "nccl"], default="peer",
                     help="N > 1: frame assembly by peer-memory stores from the compositing kernel + flag barrier (nvr_render_rays_frame) "
                          "or by the round-1 path (pad + NCCL all_gather + un-permute)")
+    ap.add_argument("--emulate-shard-of", type=int, default=0, metavar="N",
+                    help="development aid (not a bench line): on ONE GPU render only rank 0's shard of an N-rank run, i.e. the "
+                         "per-rank work of `--gpus N` without the other ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the supplementary training-step measurement")
     ap.add_argument("--no-extras", action="store_true", help="only the main workload (value, e2e, stage times, roofline)")
@@ -384,7 +387,7 @@ def cpu_state_dict(S, seed=0):
 class Workload:
     """One config's rays sharded over the ranks + the two step functions (device-resident and end-to-end)."""
 
-    def __init__(self, eng, gframe, frame_cpu, cfgd, n_views, rank, world, assemble_mode="peer"):
+    def __init__(self, eng, gframe, frame_cpu, cfgd, n_views, rank, world, assemble_mode="peer", shard_of=0):
         from instant_nvr_b200.sharding import PeerFrame, shard_indices
         from instant_nvr_b200.synthetic import make_rays
         self.eng, self.gframe, self.cfgd, self.rank, self.world = eng, gframe, cfgd, rank, world
@@ -393,7 +396,7 @@ class Workload:
         rays = {k: torch.cat([v[k][0] for v in views]).contiguous() for k in ("ray_o", "ray_d", "near", "far")}
         self.n_views, self.n_pixels = n_views, n_views * H * W
         self.n_total = rays["ray_o"].shape[0]
-        idx = shard_indices(self.n_total, rank, world)
+        idx = shard_indices(self.n_total, rank, world) if not shard_of else shard_indices(self.n_total, 0, shard_of)
         self.host = {k: v[idx].contiguous().pin_memory() for k, v in rays.items()}
         self.dev = {k: v.cuda() for k, v in self.host.items()}
         self.n_local = idx.numel()
@@ -499,7 +502,7 @@ def main():
     gframe = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in frame.items()}
     eng = net.engine()
     eng.bind_frame(gframe)
-    wl = Workload(eng, gframe, frame, cfgd, n_views, rank, world, args.assemble)
+    wl = Workload(eng, gframe, frame, cfgd, n_views, rank, world, args.assemble, args.emulate_shard_of)
 
     def timed(e, fn, steps, warmup, profile=False, mark=False):
         # mark: cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off sees exactly them)
@@ -538,12 +541,14 @@ def main():
 
     W = max(args.warmup, 3)
     if args.steps_only:
+        ms_plain, _, _, _ = timed(eng, wl.step_device, args.steps, args.warmup)
         ms, clocks, prof, launches = timed(eng, wl.step_device, args.steps, args.warmup, profile=True, mark=True)
         if rank == 0:
             emit({"metric": "ray_samples_per_sec", "value": wl.samples_per_step * args.steps / (ms * 1e-3), "unit": "ray-samples/s",
                   "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                  "ms_per_step_unprofiled": ms_plain / args.steps,
                   "gpu_launches": launches, "stage_ms_per_step": {k: v / args.steps for k, v in prof["ms"].items()},
-                  "mlp_mode": eng.mlp_mode, "tune": eng.tune, "csrc_hash": csrc_hash(),
+                  "mlp_mode": eng.mlp_mode, "tune": eng.tune, "csrc_hash": csrc_hash(), "rays_per_gpu": wl.n_local,
                   "note": "--steps-only: profiler-facing run, not a bench line"})
         if world > 1:
             dist.destroy_process_group()

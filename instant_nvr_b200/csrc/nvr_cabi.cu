@@ -425,6 +425,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
             eb.x[p] = (const float*)(w.pairs + (long long)p * w.cap);
             eb.count[p] = w.counters + NVR_CTR_PAIR + p;
             eb.out[p] = w.emb + (long long)p * w.cap * NVR_EMB_STRIDE;
+            eb.work[p] = w.counters + NVR_CTR_EMBED_WORK + p;
         }
         k_embed_parts<<<dim3(grid_for(n, 128, sm * 2), NVR_NUM_PARTS), 256, 0, st>>>(h->d_part_grid, eb, 8, NVR_EMB_STRIDE);
         h->launches -= NVR_NUM_PARTS - 1;

@@ -26,7 +26,8 @@
 #define NVR_CTR_PAIR 1             // [1..5]
 #define NVR_CTR_FAR 6              // [6..10] flagged pairs answered by the part's shared far-field pair
 #define NVR_CTR_WORK 11             // k_knn's dynamic work-unit counter
-#define NVR_CTR_WORDS 16
+#define NVR_CTR_EMBED_WORK 12       // [12..16] k_embed_parts' work-unit counters, one per part
+#define NVR_CTR_WORDS 32
 // Far-field pairs.  A part farther than ~0.73 m from a sample still gets flagged (its Gaussian weights sum to far less
 // than the 1e-8 in the normalisation, so pdist -> 0 < smpl_thresh: DESIGN.md section 1).  Once sum(w) < NVR_FAR_WSUM the
 // normalised weights are < 1e-12, the blended transforms are ~1e-12, and the canonical point and direction the part
@@ -768,13 +769,22 @@ __device__ __forceinline__ const float* level_rows(const GridDev& g, int l, int 
     return g.hash;
 }
 
+// DYN: the 16-pair units are handed out through a device counter (`work`) instead of a static grid stride, so a launch is
+// balanced when a warp only gets two or three units (a shard of a frame on one of eight GPUs)
+template <bool DYN>
 __device__ __forceinline__ void embed_body(const GridDev& g, const float* __restrict__ xb, int xstride, int n,
-                                           float* __restrict__ eb, int emb_stride, int l_begin, int l_end) {
+                                           float* __restrict__ eb, int emb_stride, int l_begin, int l_end, int* work) {
     const int lane = threadIdx.x & 31, half = lane & 1;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    auto next_unit = [&](int prev) {
+        if (!DYN) return prev + n_warps * 16;
+        int u = 0;
+        if (lane == 0) u = atomicAdd(work, 1);
+        return __shfl_sync(0xffffffffu, u, 0) * 16;
+    };
     const bool fast_mod = g.T_magic40 != 0;
     const unsigned int T32 = (unsigned int)g.T;
-    for (int base = warp * 16; base < n; base += n_warps * 16) {
+    for (int base = DYN ? next_unit(0) : warp * 16; base < n; base = next_unit(base)) {
         const int pt = base + (lane >> 1);
         const bool live = pt < n;
         const float* xp = xb + (long long)(live ? pt : n - 1) * xstride;
@@ -819,20 +829,21 @@ k_embed(GridDev g, const float* __restrict__ xb, int xstride, const int* __restr
         float* __restrict__ eb, int emb_stride, int l_begin, int l_end) {
     // levels [l_begin, l_end) only (the normalised coordinates are written by the launch with l_begin == 0): the level-major
     // experiment gathers a part one L2-sized slice of its tables per launch (nvr_cabi.cu, embed_plan)
-    embed_body(g, xb, xstride, count_dev ? *count_dev : n_imm, eb, emb_stride, l_begin, l_end);
+    embed_body<false>(g, xb, xstride, count_dev ? *count_dev : n_imm, eb, emb_stride, l_begin, l_end, nullptr);
 }
 
 // All five parts of a pass as ONE grid: blockIdx.y = part.  Same per-CTA work as five k_embed launches (a CTA gathers one part's
 // pairs, so consecutive units still share coarse-level rows in L1), but the launches' tails overlap: CTAs of part p + 1 start as
 // the last CTAs of part p drain.  The part's grid description is staged in shared memory (a run-time index into a kernel
 // parameter array would be copied to the stack).
-struct EmbedBatch { const float* x[NVR_PARTS]; const int* count[NVR_PARTS]; float* out[NVR_PARTS]; };
+struct EmbedBatch { const float* x[NVR_PARTS]; const int* count[NVR_PARTS]; float* out[NVR_PARTS]; int* work[NVR_PARTS]; };
 __global__ void __launch_bounds__(256, 2)
 k_embed_parts(const GridDev* __restrict__ grids, EmbedBatch b, int xstride, int emb_stride) {
     __shared__ GridDev sg;
     __shared__ const float* s_x;
     __shared__ const int* s_count;
     __shared__ float* s_out;
+    __shared__ int* s_work;
     const int part = blockIdx.y;
     {
         const int* src = reinterpret_cast<const int*>(grids + part);
@@ -841,11 +852,11 @@ k_embed_parts(const GridDev* __restrict__ grids, EmbedBatch b, int xstride, int 
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int p = 0; p < NVR_PARTS; ++p)
-                if (p == part) { s_x = b.x[p]; s_count = b.count[p]; s_out = b.out[p]; }
+                if (p == part) { s_x = b.x[p]; s_count = b.count[p]; s_out = b.out[p]; s_work = b.work[p]; }
         }
     }
     __syncthreads();
-    embed_body(sg, s_x, xstride, *s_count, s_out, emb_stride, 0, sg.n_levels);
+    embed_body<true>(sg, s_x, xstride, *s_count, s_out, emb_stride, 0, sg.n_levels, s_work);
 }
 
 // -----------------------------------------------------------------------------------------
