@@ -541,8 +541,8 @@ def main():
 
     W = max(args.warmup, 3)
     if args.steps_only:
-        ms_plain, _, _, _ = timed(eng, wl.step_device, args.steps, args.warmup)
-        ms, clocks, prof, launches = timed(eng, wl.step_device, args.steps, args.warmup, profile=True, mark=True)
+        ms_plain, _, _, _ = timed(eng, wl.step_device, args.steps, args.warmup, mark=bool(os.environ.get("NVR_MARK_PLAIN")))
+        ms, clocks, prof, launches = timed(eng, wl.step_device, args.steps, args.warmup, profile=True, mark=not os.environ.get("NVR_MARK_PLAIN"))
         if rank == 0:
             emit({"metric": "ray_samples_per_sec", "value": wl.samples_per_step * args.steps / (ms * 1e-3), "unit": "ray-samples/s",
                   "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,

@@ -328,6 +328,12 @@ int nvr_generate_rays(NvrHandle h, int32_t H, int32_t W, const double* K_inv_hos
  * by n and takes -10 log10 for the PSNR).  sq_sum is a device double, overwritten. */
 int nvr_assemble_image(NvrHandle h, const float* rgb, const int32_t* coord, int64_t n_rays, int64_t n_pixels, float* img, void* stream);
 int nvr_sq_diff_sum(NvrHandle h, const float* a, const float* b, int64_t n, double* sq_sum, void* stream);
+/* The evaluator's SSIM (lib/evaluators/if_nerf.py:33-74): skimage 0.19.3 structural_similarity(multichannel=True) on the
+ * float64 crop rows [y0, y0+h) x columns [x0, x0+w) (cv2.boundingRect of mask_at_box) of two (H, W, 3) fp32 images -- uniform
+ * 7 x 7 windows, sample covariance, data_range 2 (skimage's dtype range of float images), interior only.  sums (3 device
+ * doubles, overwritten) = per-channel sums of S over the (h-6) x (w-6) interior; ssim = mean_c sums[c] / ((h-6)(w-6)). */
+int nvr_ssim_sums(NvrHandle h, const float* img_a, const float* img_b, int32_t H, int32_t W, int32_t x0, int32_t y0,
+                  int32_t w, int32_t hh, double* sums, void* stream);
 
 /* -- Per-frame SMPL preprocessing (8(f) rank 3): what the reference's dataset computes in numpy for every frame
  * (lib/datasets/h36m/tpose_dataset.py:247-293 prepare_input, :570-600 part tables; get_rigid_transformation,

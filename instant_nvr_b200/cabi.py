@@ -145,6 +145,8 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nvr_assemble_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "nvr_sq_diff_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nvr_ssim_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_void_p, C.c_void_p]),
     "nvr_smpl_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "nvr_smpl_pose_frame": (C.c_int, [C.c_void_p, C.POINTER(NvrSmplPose), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
                                       C.POINTER(NvrSmplOut), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -194,3 +194,47 @@ __global__ void __launch_bounds__(256) k_sq_diff(const float* __restrict__ a, co
         atomicAdd(out, t);
     }
 }
+
+// ---- SSIM ------------------------------------------------------------------------------------------------------------
+// The evaluator's structural similarity (lib/evaluators/if_nerf.py:33-74): skimage 0.19.3 `structural_similarity(a, b,
+// multichannel=True)` on the float64 crop [y0, y0+h) x [x0, x0+w) of two (H, W, 3) images holding float32 values -- uniform
+// 7 x 7 windows, sample covariance (49/48), data_range 2 (skimage's dtype range of float images: C1 = (0.01 * 2)^2,
+// C2 = (0.03 * 2)^2), mean of S over the interior (3 pixels cropped on every side) and over the channels.
+// One thread per interior pixel and channel, window sums in float64; out[c] += sum of S over the channel's interior.
+__global__ void __launch_bounds__(256)
+k_ssim(const float* __restrict__ a, const float* __restrict__ b, int W, int x0, int y0, int w, int h, double* __restrict__ out) {
+    __shared__ double s_part[8][3];
+    const int iw = w - 6, ih = h - 6;
+    const long long n = (long long)iw * ih * 3;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % 3);
+        const long long px = i / 3;
+        const int cx = x0 + 3 + (int)(px % iw), cy = y0 + 3 + (int)(px / iw);
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        for (int dy = -3; dy <= 3; ++dy)
+            for (int dx = -3; dx <= 3; ++dx) {
+                const long long o = ((long long)(cy + dy) * W + (cx + dx)) * 3 + c;
+                const double x = a[o], y = b[o];
+                sx += x; sy += y; sxx += x * x; syy += y * y; sxy += x * y;
+            }
+        const double ux = sx / 49.0, uy = sy / 49.0, uxx = sxx / 49.0, uyy = syy / 49.0, uxy = sxy / 49.0;
+        const double cov = 49.0 / 48.0;
+        const double vx = cov * (uxx - ux * ux), vy = cov * (uyy - uy * uy), vxy = cov * (uxy - ux * uy);
+        const double C1 = 0.0004, C2 = 0.0036;
+        const double S = ((2.0 * ux * uy + C1) * (2.0 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+        acc[c] += S;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][c] = acc[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int wp = 0; wp < 8; ++wp) t += s_part[wp][threadIdx.x];
+        atomicAdd(out + threadIdx.x, t);
+    }
+}

@@ -1070,6 +1070,21 @@ extern "C" int nvr_sq_diff_sum(NvrHandle h, const float* a, const float* b, int6
     return 0;
 }
 
+extern "C" int nvr_ssim_sums(NvrHandle h, const float* img_a, const float* img_b, int32_t H, int32_t W, int32_t x0, int32_t y0,
+                             int32_t w, int32_t hh, double* sums, void* stream_) {
+    if (!h) return 1;
+    if (!img_a || !img_b || !sums || H < 1 || W < 1 || x0 < 0 || y0 < 0 || w < 1 || hh < 1 || x0 + w > W || y0 + hh > H)
+        return fail(h, "nvr_ssim_sums: bad argument");
+    if (w < 7 || hh < 7) return fail(h, "nvr_ssim_sums: the crop must be at least 7 x 7 (win_size exceeds image extent)");
+    NVR_CHECK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream_;
+    NVR_CHECK(h, cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
+    k_ssim<<<grid_for((long long)(w - 6) * (hh - 6) * 3, 256, h->sm_count * 8), 256, 0, st>>>(img_a, img_b, W, x0, y0, w, hh, sums);
+    NVR_CHECK(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
 // ---- per-frame SMPL preprocessing ---------------------------------------------------------
 extern "C" size_t nvr_smpl_workspace_bytes(int32_t n_verts) {
     return n_verts < 0 ? 0 : (size_t)SMPL_WS_PXYZ + (size_t)n_verts * 3 * sizeof(double);

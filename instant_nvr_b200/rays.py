@@ -4,9 +4,9 @@ reference's names and argument meaning:
 * ``get_rays_within_bounds`` / ``get_rays_within_bounds_coord`` -- ``lib/utils/if_nerf/if_nerf_data_utils.py:329-362``
   (``get_rays`` :24-38 + ``get_near_far`` :92-107 + the ``mask_at_box`` compaction), numpy on DataLoader workers in
   the reference, one call per rendered frame (``tpose_dataset.py:438``, ``tpose_novel_view_dataset.py:206``);
-* ``assemble_image`` / ``psnr_metric`` -- ``lib/evaluators/if_nerf.py:28-31, 84-113``.
+* ``assemble_image`` / ``psnr_metric`` / ``ssim_metric`` -- ``lib/evaluators/if_nerf.py:28-31, 33-74, 84-113``.
 
-All arithmetic runs in ``libnvr_b200.so`` (``nvr_generate_rays``, ``nvr_assemble_image``, ``nvr_sq_diff_sum``); outputs
+All arithmetic runs in ``libnvr_b200.so`` (``nvr_generate_rays``, ``nvr_assemble_image``, ``nvr_sq_diff_sum``, ``nvr_ssim_sums``); outputs
 are CUDA tensors, so a novel-view render needs no host round trip between ray generation, the render and the metric.
 """
 from __future__ import annotations
@@ -103,3 +103,29 @@ def psnr_metric(img_pred: torch.Tensor, img_gt: torch.Tensor) -> float:
     """``-10 * log(mse) / log(10)`` (evaluators/if_nerf.py:28-31)."""
     mse = mse_metric(img_pred, img_gt)
     return -10.0 * math.log(mse) / math.log(10.0) if mse > 0 else float("inf")
+
+
+def ssim_metric(img_pred: torch.Tensor, img_gt: torch.Tensor, mask_at_box: torch.Tensor) -> float:
+    """``Evaluator.ssim_metric`` (evaluators/if_nerf.py:33-74) without the numpy / cv2 round trip: the two assembled (H,W,3)
+    images are cropped to ``cv2.boundingRect(mask_at_box)`` and compared with skimage 0.19.3's
+    ``structural_similarity(multichannel=True)`` (uniform 7x7 windows, sample covariance, data_range 2, interior mean)."""
+    H, W = mask_at_box.shape
+    device = img_pred.device
+    lib, h = aux_handle(device)
+    a = img_pred.to(torch.float32).contiguous()
+    b = img_gt.to(device=device, dtype=torch.float32).contiguous()
+    if a.shape != (H, W, 3) or b.shape != (H, W, 3):
+        raise ValueError("images must be (H, W, 3) like mask_at_box")
+    m = mask_at_box.to(device)
+    rows, cols = m.any(dim=1).nonzero(as_tuple=True)[0], m.any(dim=0).nonzero(as_tuple=True)[0]
+    if rows.numel() == 0:
+        raise ValueError("empty mask_at_box")
+    y0, y1, x0, x1 = int(rows[0]), int(rows[-1]), int(cols[0]), int(cols[-1])      # cv2.boundingRect of the mask
+    w, hh = x1 - x0 + 1, y1 - y0 + 1
+    if w < 7 or hh < 7:
+        raise ValueError("win_size exceeds image extent")                            # what skimage raises
+    out = torch.empty(3, dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        check(lib, h, lib.nvr_ssim_sums(h, a.data_ptr(), b.data_ptr(), H, W, x0, y0, w, hh, out.data_ptr(),
+                                        torch.cuda.current_stream(device).cuda_stream), "nvr_ssim_sums")
+    return float((out / float((w - 6) * (hh - 6))).mean().item())

@@ -61,3 +61,35 @@ def assemble_image(rgb, mask_at_box):
     img = np.zeros(mask_at_box.shape + (3,))
     img[mask_at_box] = rgb
     return img
+
+
+def ssim(img_pred, img_gt, mask_at_box):
+    """Evaluator.ssim_metric (lib/evaluators/if_nerf.py:33-74) minus its file output: crop both (H,W,3) float64 images to
+    cv2.boundingRect(mask_at_box) (:68-71) and call skimage's compare_ssim(multichannel=True) (:73).
+
+    skimage is a third-party dependency absent from /root/reference (requirements.txt pins scikit-image==0.19.3) and from
+    this image, so ``structural_similarity`` is RESTATED here from its published source (skimage/metrics/_structural_similarity.py
+    @ v0.19.3): win_size 7, uniform_filter means (scipy.ndimage, as skimage does), sample covariance NP/(NP-1), data_range =
+    dtype_range[float64] = 2, K1 0.01, K2 0.03, mean of S cropped by (win_size-1)//2, mean over channels.  PARITY UNPINNED against
+    skimage itself (it cannot be imported here); the restatement is checked against a direct windowed evaluation."""
+    import numpy as np
+    from scipy.ndimage import uniform_filter
+    m = np.asarray(mask_at_box, dtype=bool)
+    rows, cols = np.nonzero(m.any(1))[0], np.nonzero(m.any(0))[0]
+    y, x, h, w = rows[0], cols[0], rows[-1] - rows[0] + 1, cols[-1] - cols[0] + 1
+    a = np.asarray(img_pred, dtype=np.float64)[y:y + h, x:x + w]
+    b = np.asarray(img_gt, dtype=np.float64)[y:y + h, x:x + w]
+    win, K1, K2, R = 7, 0.01, 0.03, 2.0
+    NP = win ** 2
+    cov_norm = NP / (NP - 1)
+    C1, C2 = (K1 * R) ** 2, (K2 * R) ** 2
+    pad = (win - 1) // 2
+    vals = []
+    for c in range(a.shape[2]):
+        x1, y1 = a[..., c], b[..., c]
+        ux, uy = uniform_filter(x1, size=win), uniform_filter(y1, size=win)
+        uxx, uyy, uxy = uniform_filter(x1 * x1, size=win), uniform_filter(y1 * y1, size=win), uniform_filter(x1 * y1, size=win)
+        vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+        S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+        vals.append(S[pad:-pad, pad:-pad].mean(dtype=np.float64))
+    return float(np.mean(vals))

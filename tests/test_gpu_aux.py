@@ -215,3 +215,27 @@ def test_rays_feed_the_renderer(golden_setup):
     want = RO.psnr_metric(img.cpu().numpy(), gt.numpy())
     assert ours == pytest.approx(want, rel=1e-9)
     assert abs(ours - RO.psnr_metric(img_ref, gt.numpy())) < 0.1          # north_star: PSNR within 0.1 dB
+
+
+def test_ssim_metric_matches_oracle():
+    """rays.ssim_metric (nvr_ssim_sums) against the numpy oracle of the evaluator's SSIM (skimage 0.19.3 restated): assembled
+    images of a render-sized frame, ragged crops, identical images."""
+    import numpy as np
+    import rays_oracle as RO
+    from instant_nvr_b200.rays import ssim_metric
+    g = torch.Generator().manual_seed(5)
+    for (H, W, box) in ((64, 80, (5, 60, 7, 71)), (512, 512, (37, 480, 100, 401)), (9, 9, (0, 9, 0, 9))):
+        a = torch.rand(H, W, 3, generator=g)
+        b = (a + 0.05 * torch.randn(H, W, 3, generator=g)).clamp(0, 1)
+        m = torch.zeros(H, W, dtype=torch.bool)
+        m[box[0]:box[1], box[2]:box[3]] = True
+        a[~m] = 0
+        b[~m] = 0
+        ref = RO.ssim(a.numpy(), b.numpy(), m.numpy())
+        ours = ssim_metric(a.cuda(), b.cuda(), m.cuda())
+        assert abs(ours - ref) < 1e-10, (H, W, ours, ref)
+        assert abs(ssim_metric(a.cuda(), a.cuda(), m.cuda()) - 1.0) < 1e-12
+    with pytest.raises(ValueError):
+        m = torch.zeros(32, 32, dtype=torch.bool)
+        m[3:8, 3:20] = True                                  # 5 rows: smaller than the 7 x 7 window
+        ssim_metric(torch.rand(32, 32, 3).cuda(), torch.rand(32, 32, 3).cuda(), m.cuda())

@@ -110,3 +110,32 @@ def test_device_adam_math_matches_torch(emul, wd, steps):
         assert np.all(np.abs(m - m_ref) <= 2e-6 * np.abs(m_ref) + 2e-7 * gmax)
         assert np.all(np.abs(v - v_ref) <= 2e-6 * np.abs(v_ref) + 4e-7 * (1 - 0.999) * gmax ** 2)
         np.testing.assert_allclose(p, p_ref.detach().numpy(), rtol=1.2e-7, atol=4e-9)           # one ulp of p + the update's own rounding
+
+
+def test_ssim_oracle_matches_direct_windowed_evaluation():
+    """oracle ssim (skimage 0.19.3 structural_similarity restated over scipy's uniform_filter, as skimage computes it) against a
+    direct per-window evaluation of the published formula; plus the identities SSIM(a, a) = 1 and symmetry."""
+    import numpy as np
+    import rays_oracle as RO
+    rng = np.random.default_rng(0)
+    H, W = 40, 50
+    a = rng.random((H, W, 3)).astype(np.float32).astype(np.float64)
+    b = np.clip(a + 0.1 * rng.standard_normal((H, W, 3)), 0, 1).astype(np.float32).astype(np.float64)
+    m = np.zeros((H, W), bool)
+    m[5:33, 8:41] = True
+    s = RO.ssim(a, b, m)
+    aa, bb = a[5:33, 8:41], b[5:33, 8:41]
+    vals = []
+    for c in range(3):
+        tot, cnt = 0.0, 0
+        for y in range(3, aa.shape[0] - 3):
+            for x in range(3, aa.shape[1] - 3):
+                wa, wb = aa[y - 3:y + 4, x - 3:x + 4, c], bb[y - 3:y + 4, x - 3:x + 4, c]
+                ux, uy = wa.mean(), wb.mean()
+                k = 49 / 48
+                vx, vy, vxy = k * ((wa * wa).mean() - ux * ux), k * ((wb * wb).mean() - uy * uy), k * ((wa * wb).mean() - ux * uy)
+                tot += ((2 * ux * uy + 4e-4) * (2 * vxy + 3.6e-3)) / ((ux * ux + uy * uy + 4e-4) * (vx + vy + 3.6e-3))
+                cnt += 1
+        vals.append(tot / cnt)
+    assert abs(s - np.mean(vals)) < 1e-12
+    assert abs(RO.ssim(a, a, m) - 1.0) < 1e-12 and abs(RO.ssim(b, a, m) - s) < 1e-12
