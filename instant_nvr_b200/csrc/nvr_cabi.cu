@@ -16,6 +16,7 @@
 #include "nvr_smpl.cuh"
 #include "nvr_mlp_tc.cuh"
 #include "nvr_mlp_f16.cuh"
+#include "nvr_warp_tc.cuh"
 #include "nvr_train.cuh"
 #include "nvr_aux.cuh"
 
@@ -404,11 +405,17 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     else
         k_knn<4><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot); }
     { StageTimer t(h, st, NVR_STAGE_WARP);
+    if (!(h->cfg.tune & (NVR_TUNE_WARP_FFMA | NVR_TUNE_WARP_OCC4))) {
+        // default: deformer MLP on tcgen05, one 128-pair tile per CTA iteration (nvr_warp_tc.cuh)
+        const dim3 wg(grid_for(n, WT_THREADS, sm * 3 / 2), NVR_NUM_PARTS);
+        k_warp_tc<<<wg, WT_THREADS, WT_SMEM_BYTES, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap,
+                                                         dbg, out_x0, out_resd, rank_of_slot);
+    } else {
     const dim3 wg(grid_for(n, WARP_THREADS, sm * 3), NVR_NUM_PARTS);
     if (!(h->cfg.tune & NVR_TUNE_WARP_OCC4))    // <= 64 registers: 8 CTAs (32 warps) per SM instead of 4
         k_warp<8><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd, rank_of_slot);
     else
-        k_warp<1><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd, rank_of_slot); }
+        k_warp<1><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd, rank_of_slot); } }
     const bool tc = h->cfg.mlp_mode >= 1;
     if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
         StageTimer t(h, st, NVR_STAGE_MLP);

@@ -241,16 +241,17 @@ NVR_HD void nvr_embed_point(const GridDev& g, const float x[3], float* out, int 
 }
 
 
-#ifdef __CUDA_ARCH__
+#ifdef __CUDACC__
 // Device form of nvr_embed_point<2> in concat mode (the deformer grid: 8 levels x 2 features, 19 outputs): the same values
 // in the same order -- clamped corners, weights, accumulation over the corners c = 0..7 -- with 32-bit index arithmetic
 // (cvt.rzi + clamp == .long() + clamp, products < 2^40 reduced by nvr_mod_T40) and the 8 corner rows of a level fetched as
 // independent 8-byte loads before the first multiply (ncu r2a: the scalar form spent 17 % of k_warp's stall samples waiting
 // on one dependent row load after another and 14 % of its instructions on 64-bit row arithmetic).
-__device__ __forceinline__ void nvr_embed_point_f2_dev(const GridDev& g, const float x[3], float* out, int os) {
+template <class Emit>
+__device__ __forceinline__ void nvr_embed_point_f2_emit(const GridDev& g, const float x[3], Emit emit) {   // emit(k, value), k < 19
     float u[3];
     nvr_normalise(g, x, u);
-    out[0] = u[0]; out[os] = u[1]; out[2 * os] = u[2];
+    emit(0, u[0]); emit(1, u[1]); emit(2, u[2]);
     const bool fast_mod = g.T_magic40 != 0;
     const unsigned int T32 = (unsigned int)g.T;
 #pragma unroll 1
@@ -298,8 +299,11 @@ __device__ __forceinline__ void nvr_embed_point_f2_dev(const GridDev& g, const f
             const float w = (wx[(c >> 2) & 1] * wy[(c >> 1) & 1]) * wz[c & 1];   // :158-159
             a0 += w * v[c].x; a1 += w * v[c].y;                                    // :160
         }
-        out[(3 + l * 2) * os] = a0; out[(3 + l * 2 + 1) * os] = a1;               // :169
+        emit(3 + l * 2, a0); emit(3 + l * 2 + 1, a1);                            // :169
     }
+}
+__device__ __forceinline__ void nvr_embed_point_f2_dev(const GridDev& g, const float x[3], float* out, int os) {
+    nvr_embed_point_f2_emit(g, x, [&](int k, float v) { out[k * os] = v; });
 }
 #endif
 
