@@ -28,18 +28,29 @@ def trainable(net) -> List[Tuple[str, torch.nn.Parameter]]:
     return cached
 
 
+_ZERO_PLANS: Dict[tuple, tuple] = {}
+
+
 def zero_grads(params: Dict[str, torch.Tensor], names: List[str]) -> Dict[str, torch.Tensor]:
     """Fresh zero-filled gradient buffers for ``names``: ONE allocation and ONE fill launch (the 67 trainable tensors
     are views of it at 256-byte-aligned offsets) instead of one of each per tensor.  A new buffer every call: autograd
     takes ownership of what a backward returns (``.grad`` may alias it), so it must not be reused.  The returned dict
     carries the flat buffer's address under ``"_base"`` (engine: the gradient descriptor is cached per address)."""
-    offs, total = [], 0
-    for name in names:
-        offs.append(total)
-        total += (params[name].numel() + 63) & ~63
+    key = (id(params), len(names))
+    plan = _ZERO_PLANS.get(key, None)
+    if plan is None or plan[0] != tuple(names):
+        offs, total = [], 0
+        for name in names:
+            offs.append(total)
+            total += (params[name].numel() + 63) & ~63
+        plan = (tuple(names), total, [(name, tuple(params[name].shape), params[name].stride(), o) for name, o in zip(names, offs)])
+        if len(_ZERO_PLANS) > 8:
+            _ZERO_PLANS.clear()
+        _ZERO_PLANS[key] = plan
+    total = plan[1]
     ref = params[names[0]]
     flat = torch.zeros(total, dtype=torch.float32, device=ref.device)
-    out = {name: flat[o:o + params[name].numel()].view(params[name].shape) for name, o in zip(names, offs)}
+    out = {name: flat.as_strided(shape, stride, off) for name, shape, stride, off in plan[2]}     # one view op per tensor
     out["_base"] = (flat.data_ptr(), total, len(names))
     return out
 
