@@ -233,12 +233,11 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
     const size_t max_cl = (size_t)NVR_NUM_PARTS * ((f->maxlen + NVR_CL - 1) / NVR_CL);
     const size_t n_verts = max_cl * NVR_CL + 2 * max_cl;   // float4 slots: vertices, then cl_lo, then cl_hi
     const size_t n_coarse = (size_t)nvr_coarse_dim(f->pbw_dims[0]) * nvr_coarse_dim(f->pbw_dims[1]) * nvr_coarse_dim(f->pbw_dims[2]);
-    const size_t n_coarse2 = (size_t)nvr_coarse2_dim(f->pbw_dims[0]) * nvr_coarse2_dim(f->pbw_dims[1]) * nvr_coarse2_dim(f->pbw_dims[2]);
-    if (n_vox + n_coarse + n_coarse2 > h->dist_cap) {
+    if (n_vox + n_coarse > h->dist_cap) {
         NVR_CHECK(h, cudaFree(h->d_dist));
         h->d_dist = nullptr; h->dist_cap = 0;
-        NVR_CHECK(h, cudaMalloc(&h->d_dist, (n_vox + n_coarse + n_coarse2) * sizeof(float)));
-        h->dist_cap = n_vox + n_coarse + n_coarse2;
+        NVR_CHECK(h, cudaMalloc(&h->d_dist, (n_vox + n_coarse) * sizeof(float)));
+        h->dist_cap = n_vox + n_coarse;
     }
     if (n_verts > h->verts_cap) {
         NVR_CHECK(h, cudaFree(h->d_verts));
@@ -258,9 +257,7 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
     float* d_cmin = h->d_dist + n_vox;
     k_frame_coarse<<<std::min<int>(h->sm_count * 8, (int)((n_coarse + 3) / 4)), 128, 0, stream>>>(
         h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], d_cmin);
-    float* d_cmin2 = d_cmin + n_coarse;
-    k_frame_coarse2<<<std::max<int>(1, (int)((n_coarse2 + 127) / 128)), 128, 0, stream>>>(d_cmin, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], d_cmin2);
-    h->launches += 2;
+    h->launches++;
     float4* cl_lo = h->d_verts + max_cl * NVR_CL;
     float4* cl_hi = cl_lo + max_cl;
     if (f->topology_key == 0 || f->topology_key != h->perm_key || f->maxlen != h->perm_maxlen) {
@@ -278,7 +275,6 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
     d.R = f->R; d.Th = f->Th;
     d.dist = VolumeDev{h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], 1, f->pbounds};
     d.dist_cmin = (h->cfg.tune & NVR_TUNE_NO_CULL_EARLY_OUT) ? nullptr : d_cmin;
-    d.dist_cmin2 = (h->cfg.tune & (NVR_TUNE_NO_CULL_EARLY_OUT | NVR_TUNE_NO_CULL_SEGMENTS)) ? nullptr : d_cmin2;
     d.tuv = VolumeDev{f->tuv, f->tuv_dims[0], f->tuv_dims[1], f->tuv_dims[2], 2, f->tbounds};
     d.verts = h->d_verts; d.cl_lo = cl_lo; d.cl_hi = cl_hi; d.cl_off = h->d_cl_off; d.part_pbw = f->part_pbw; d.maxlen = f->maxlen;
     d.A = f->A; d.bigA = f->big_A; d.frame_dim = f->frame_dim; d.latent_index = (const long long*)f->latent_index;

@@ -59,7 +59,6 @@ struct FrameDev {                  // per-frame tensors as the kernels see them
     const float* Th;
     VolumeDev dist;                // compact (D,H,W,1) distance volume
     const float* dist_cmin;        // per coarse cell minimum of dist (nvr_cull_early_out); null = no early-out
-    const float* dist_cmin2;       // its second level: minimum over blocks of 4^3 coarse cells (nvr_cull_segment)
     VolumeDev tuv;                 // (D',H',W',2)
     const float4* verts;           // part vertices, spatially sorted: one 16-float4 SoA block per cluster (x | y | z | orig index)
     const float4* cl_lo;           // per-cluster AABB
@@ -115,23 +114,6 @@ k_frame_coarse(const float* __restrict__ dist, int D, int H, int W, float* __res
         for (int s = 16; s > 0; s >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, s));
         nan = __any_sync(0xffffffffu, nan);
         if (lane == 0) cmin[i] = nan ? __int_as_float(0x7fc00000) : m;
-    }
-}
-
-// second level: minimum of cmin over blocks of NVR_CULL_B2^3 coarse cells (a NaN cell poisons its block)
-__global__ void k_frame_coarse2(const float* __restrict__ cmin, int D, int H, int W, float* __restrict__ cmin2) {
-    const int cD = nvr_coarse_dim(D), cH = nvr_coarse_dim(H), cW = nvr_coarse_dim(W);
-    const int D2 = nvr_coarse2_dim(D), H2 = nvr_coarse2_dim(H), W2 = nvr_coarse2_dim(W);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D2 * H2 * W2; i += gridDim.x * blockDim.x) {
-        const int bz = i / (H2 * W2), by = (i / W2) % H2, bx = i % W2;
-        float m = INFINITY;
-        for (int z = bz * NVR_CULL_B2; z < min(bz * NVR_CULL_B2 + NVR_CULL_B2, cD); ++z)
-            for (int y = by * NVR_CULL_B2; y < min(by * NVR_CULL_B2 + NVR_CULL_B2, cH); ++y)
-                for (int x = bx * NVR_CULL_B2; x < min(bx * NVR_CULL_B2 + NVR_CULL_B2, cW); ++x) {
-                    const float d = cmin[(z * cH + y) * cW + x];
-                    m = (d < m || d != d) ? d : m;
-                }
-        cmin2[i] = m;
     }
 }
 
@@ -404,8 +386,6 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
     const long long n_map = rays ? ((cw.n_rays + 31) / 32) * (long long)cw.group : n;
     __shared__ CullQuick cq;                                      // uniform: one copy per CTA, broadcast reads
     const bool quick = fr.dist_cmin != nullptr && !keep_all;
-    // a warp's 8 positions per lane are 8 consecutive depth steps of ONE ray iff the samples per ray are a multiple of 8
-    const bool seg_test = quick && rays && fr.dist_cmin2 != nullptr && (n_samples % CULL_T) == 0;
     if (quick && threadIdx.x == 0) nvr_cull_quick_setup(fr.dist, fr.R, fr.Th, cq);
     __syncthreads();
     for (long long sbase = (long long)blockIdx.x * CULL_SPAN; sbase < n_map; sbase += (long long)gridDim.x * CULL_SPAN) {
@@ -416,32 +396,8 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
         int run = 0;                                              // survivors of this warp so far (warp-uniform)
         long long r_have = -1;                                    // the ray whose data the registers below hold
         float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, nr = 0.f, fa = 0.f, qa[3] = {0.f, 0.f, 0.f}, qb[3] = {0.f, 0.f, 0.f};
-        // the warp's 8 depth steps of its 32 rays as ONE segment per ray (lane): if the second-level grid says the whole
-        // segment is far from the body, none of its samples is looked at; a warp whose 32 segments are all far skips the span
-        bool seg_far = false;
-        if (seg_test) {
-            const int local0 = wid * CULL_T * 32 + lane;
-            long long r0 = 0, i0 = 0;
-            int k0 = 0;
-            if (cull_locate(cw, local0, r0, k0, i0) && sbase + local0 < n_map) {
-                r_have = r0;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) { o[a] = pts[r0 * 3 + a]; d[a] = ray_d[r0 * 3 + a]; }
-                nr = near_[r0]; fa = far_[r0];
-                nvr_cull_quick_ray(cq, o, d, qa, qb);
-                const float ta = nvr_linspace01(k0, n_samples), tb = nvr_linspace01(min(k0 + CULL_T - 1, n_samples - 1), n_samples);
-                const float za = nr * (1.0f - ta) + fa * ta, zb = nr * (1.0f - tb) + fa * tb;
-                float c0[3], c1[3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) { c0[a] = qa[a] + za * qb[a]; c1[a] = qa[a] + zb * qb[a]; }
-                seg_far = nvr_cull_segment(fr.dist, cq, fr.dist_cmin2, c0, c1, thresh);
-            } else {
-                seg_far = true;                                   // no ray here: nothing to keep
-            }
-        }
-        const bool skip_span = seg_test && __all_sync(0xffffffffu, seg_far);
 #pragma unroll 1
-        for (int t = 0; t < (skip_span ? 0 : CULL_T); ++t) {
+        for (int t = 0; t < CULL_T; ++t) {
             const int local = (wid * CULL_T + t) * 32 + lane;
             long long i = sbase + local, r = 0;                   // i = sample id
             int k = 0;
@@ -460,9 +416,7 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
                         nr = near_[r]; fa = far_[r];
                         if (quick) nvr_cull_quick_ray(cq, o, d, qa, qb);
                     }
-                    if (seg_far) {
-                        culled = true;
-                    } else if (quick) {
+                    if (quick) {
                         const float tk = nvr_linspace01(k, n_samples);
                         const float z = nr * (1.0f - tk) + fa * tk;
 #pragma unroll

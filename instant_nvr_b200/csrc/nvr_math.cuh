@@ -409,30 +409,6 @@ NVR_HD bool nvr_cull_quick(const VolumeDev& v, const CullQuick& q, const float* 
     return m > thresh * NVR_CULL_MARGIN;
 }
 
-// Second level of the same test, for a whole SEGMENT of a ray: voxel coordinates are affine in the depth z, so the samples of
-// a run of consecutive depth steps lie on the straight segment between its end points c0 and c1.  cmin2 holds the minimum of
-// the coarse-minimum grid over blocks of NVR_CULL_B2^3 coarse cells (so it inherits their one-voxel margins); when every
-// block the segment's bounding box touches is farther than the threshold, every sample of the run fails the per-sample quick
-// test too and the run is skipped without looking at its samples.  Runs whose box spans more than 8 blocks are not decided.
-#define NVR_CULL_B2 4                                              // coarse cells per second-level block, per axis (16 voxels)
-NVR_HD int nvr_coarse2_dim(int d) { return (nvr_coarse_dim(d) + NVR_CULL_B2 - 1) / NVR_CULL_B2; }
-NVR_HD bool nvr_cull_segment(const VolumeDev& v, const CullQuick& q, const float* cmin2, const float c0[3], const float c1[3], float thresh) {
-    int lo[3], hi[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float l = fminf(fmaxf(fminf(c0[a], c1[a]), 0.0f), q.cmax[a]), h = fminf(fmaxf(fmaxf(c0[a], c1[a]), 0.0f), q.cmax[a]);
-        lo[a] = (int)l / (NVR_CULL_B * NVR_CULL_B2);
-        hi[a] = (int)h / (NVR_CULL_B * NVR_CULL_B2);
-    }
-    if ((hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1) > 8) return false;
-    const int H2 = nvr_coarse2_dim(v.H), W2 = nvr_coarse2_dim(v.W);
-    bool far = true;
-    for (int z = lo[0]; z <= hi[0]; ++z)
-        for (int y = lo[1]; y <= hi[1]; ++y)
-            for (int x = lo[2]; x <= hi[2]; ++x) far = far && cmin2[(z * H2 + y) * W2 + x] > thresh * NVR_CULL_MARGIN;
-    return far;
-}
-
 // k_cull's depth-major walk over the samples of a pass (csrc/nvr_kernels.cuh):
 // position inside the walk -> (ray, step, sample id).  g0 / w0: group index and offset of the CTA's first position
 // (one 64-bit division per 2048 positions); everything per position is 32-bit.
