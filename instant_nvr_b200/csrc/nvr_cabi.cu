@@ -252,12 +252,7 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
         h->perm_cap = max_cl * NVR_CL;
     }
     StageTimer tm_(h, stream, NVR_STAGE_PREP);
-    k_frame_prep<<<std::min<int>(h->sm_count * 4, (int)((n_vox + 255) / 256)), 256, 0, stream>>>(
-        f->pbw, (int)n_vox, f->pbw_channels, h->d_dist);
     float* d_cmin = h->d_dist + n_vox;
-    k_frame_coarse<<<std::min<int>(h->sm_count * 8, (int)((n_coarse + 3) / 4)), 128, 0, stream>>>(
-        h->d_dist, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2], d_cmin);
-    h->launches++;
     float4* cl_lo = h->d_verts + max_cl * NVR_CL;
     float4* cl_hi = cl_lo + max_cl;
     if (f->topology_key == 0 || f->topology_key != h->perm_key || f->maxlen != h->perm_maxlen) {
@@ -266,10 +261,16 @@ extern "C" int nvr_bind_frame(NvrHandle h, const NvrFrame* f, void* stream_) {
         h->perm_key = f->topology_key; h->perm_maxlen = f->maxlen;
         h->launches++;
     }
-    k_cluster_apply<<<std::max<int>(1, (int)((max_cl * NVR_CL + 127) / 128)), 128, 0, stream>>>(f->part_pts, f->maxlen, h->d_perm, h->d_cl_off,
-                                                                                             h->d_verts, cl_lo, cl_hi);
+    {   // distance channel copy | coarse minimum grid | cluster re-posing: one launch (k_frame_all)
+        const int nb_prep = std::max<int>(1, std::min<int>(h->sm_count * 2, (int)((n_vox + 511) / 512)));
+        const int nb_coarse = std::max<int>(1, std::min<int>(h->sm_count * 4, (int)((n_coarse + 3) / 4)));
+        const int nb_apply = std::max<int>(1, (int)((max_cl * NVR_CL + 127) / 128));
+        k_frame_all<<<nb_prep + nb_coarse + nb_apply, 128, 0, stream>>>(f->pbw, f->pbw_channels, f->pbw_dims[0], f->pbw_dims[1], f->pbw_dims[2],
+                                                                       h->d_dist, d_cmin, f->part_pts, f->maxlen, h->d_perm, h->d_cl_off,
+                                                                       h->d_verts, cl_lo, cl_hi, nb_prep, nb_coarse);
+    }
     NVR_CHECK(h, cudaGetLastError());
-    h->launches += 2;
+    h->launches += 1;
     h->frame = *f;
     FrameDev& d = h->fdev;
     d.R = f->R; d.Th = f->Th;
@@ -403,7 +404,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     else if (h->cfg.tune & NVR_TUNE_KNN_OCC5)   // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
         k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot);
     else
-        k_knn<4><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot); }
+        k_knn<4><<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot); }   // work-counter loop: one wave of resident CTAs
     { StageTimer t(h, st, NVR_STAGE_WARP);
     if (!(h->cfg.tune & (NVR_TUNE_WARP_FFMA | NVR_TUNE_WARP_OCC4))) {
         // default: deformer MLP on tcgen05, one 128-pair tile per CTA iteration (nvr_warp_tc.cuh)

@@ -1,10 +1,10 @@
 // nvr_kernels.cuh -- the sm_100a kernels of the per-ray hot path.
 //
-//   k_frame_prep   per frame: distance channel of pbw -> compact volume; k_frame_coarse: its coarse-minimum grid
+//   k_frame_all    per frame, one launch: distance channel of pbw -> compact volume | its coarse-minimum grid | cluster re-posing
 //   k_cull         sample gen (ray mode, depth-major walk) / point fetch, quick world-space cull, world->pose,
 //                  exact distance cull, per-warp compaction in shared memory, one atomic per 2048 positions
 //   k_cluster_verts per frame: balanced KD partition of each part's vertices into clusters + AABBs
-//                  (the KNN acceleration structure); k_cluster_apply re-poses it every frame
+//                  (the KNN acceleration structure); k_frame_all's cluster blocks re-pose it every frame
 //   k_knn          per survivor: 5x exact K=4 NN (group search over the clusters; whole-warp short cuts for far-field
 //                  and certainly-unflagged parts), Gaussian weights, per-part append of flagged (sample, part)
 //                  neighbour records; far-field pairs are answered by one shared pair per part
@@ -84,19 +84,19 @@ struct PartMlpDev {
 // -----------------------------------------------------------------------------------------
 // per-frame preparation
 // -----------------------------------------------------------------------------------------
-__global__ void k_frame_prep(const float* __restrict__ pbw, int n_vox, int C, float* __restrict__ dist) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+__device__ __forceinline__ void frame_prep_part(const float* __restrict__ pbw, int n_vox, int C, float* __restrict__ dist, int bid, int nb) {
+    const int tid = bid * blockDim.x + threadIdx.x, nth = nb * blockDim.x;
     for (int i = tid; i < n_vox; i += nth) dist[i] = pbw[(long long)i * C + (C - 1)];
 }
 
-// coarse minimum grid of the compact distance volume: one WARP per coarse cell, the lanes share out the up to 6^3 voxels
-// nvr_coarse_min visits (same set, same NaN rule: a NaN voxel poisons the cell), then a shuffle minimum
-__global__ void __launch_bounds__(128)
-k_frame_coarse(const float* __restrict__ dist, int D, int H, int W, float* __restrict__ cmin) {
+// coarse minimum grid of the distance channel: one WARP per coarse cell, the lanes share out the up to 6^3 voxels
+// nvr_coarse_min visits (same set, same NaN rule: a NaN voxel poisons the cell), then a shuffle minimum.  Reads the channel
+// straight from pbw (stride C), so it does not depend on the compact copy made next to it.
+__device__ __forceinline__ void frame_coarse_part(const float* __restrict__ pbw, int C, int D, int H, int W, float* __restrict__ cmin, int bid, int nb) {
     const int cD = nvr_coarse_dim(D), cH = nvr_coarse_dim(H), cW = nvr_coarse_dim(W);
     const int lane = threadIdx.x & 31;
     const int n_cells = cD * cH * cW;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_cells; i += (gridDim.x * blockDim.x) >> 5) {
+    for (int i = (bid * blockDim.x + threadIdx.x) >> 5; i < n_cells; i += (nb * blockDim.x) >> 5) {
         const int cz = i / (cH * cW), cy = (i / cW) % cH, cx = i % cW;
         const int z0 = cz * NVR_CULL_B > 0 ? cz * NVR_CULL_B - 1 : 0, z1 = min(cz * NVR_CULL_B + NVR_CULL_B + 1, D - 1);
         const int y0 = cy * NVR_CULL_B > 0 ? cy * NVR_CULL_B - 1 : 0, y1 = min(cy * NVR_CULL_B + NVR_CULL_B + 1, H - 1);
@@ -106,7 +106,7 @@ k_frame_coarse(const float* __restrict__ dist, int D, int H, int W, float* __res
         bool nan = false;
         for (int t = lane; t < nz * ny * nx; t += 32) {
             const int z = z0 + t / (ny * nx), y = y0 + (t / nx) % ny, x = x0 + t % nx;
-            const float d = dist[((long long)z * H + y) * W + x];
+            const float d = pbw[(((long long)z * H + y) * W + x) * C + (C - 1)];
             nan |= d != d;
             m = fminf(m, d);
         }
@@ -231,13 +231,12 @@ k_cluster_verts(const float* __restrict__ part_pts, const long long* __restrict_
 
 // Every frame: gather the posed vertices into cluster order and recompute the cluster AABBs.
 // 16 lanes per cluster (NVR_CL == 16): lane = slot, min/max by shuffles inside the half-warp.
-__global__ void __launch_bounds__(128)
-k_cluster_apply(const float* __restrict__ part_pts, int maxlen, const int* __restrict__ perm, const int* __restrict__ cl_off,
-                float4* __restrict__ verts, float4* __restrict__ cl_lo, float4* __restrict__ cl_hi) {
-    static_assert(NVR_CL == 16, "k_cluster_apply maps one half-warp to one cluster");
+__device__ __forceinline__ void cluster_apply_part(const float* __restrict__ part_pts, int maxlen, const int* __restrict__ perm, const int* __restrict__ cl_off,
+                float4* __restrict__ verts, float4* __restrict__ cl_lo, float4* __restrict__ cl_hi, int bid, int nb) {
+    static_assert(NVR_CL == 16, "cluster_apply maps one half-warp to one cluster");
     const int total = cl_off[NVR_PARTS];
     const int lane16 = threadIdx.x & 15;
-    for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; c < ((total + 1) & ~1); c += (gridDim.x * blockDim.x) >> 4) {
+    for (int c = (bid * blockDim.x + threadIdx.x) >> 4; c < ((total + 1) & ~1); c += (nb * blockDim.x) >> 4) {
         const bool in = c < total;                                 // clusters are handled in warp-wide pairs
         int part = 0;
 #pragma unroll
@@ -268,6 +267,19 @@ k_cluster_apply(const float* __restrict__ part_pts, int maxlen, const int* __res
             cl_hi[c] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
     }
+}
+
+// The three per-frame preparation steps are independent of each other (the coarse grid reads pbw directly), so they are ONE
+// launch: blocks [0, nb_prep) copy the distance channel, [nb_prep, nb_prep + nb_coarse) build the coarse minimum grid, the rest
+// re-pose the vertex clusters.  128 threads per block.
+__global__ void __launch_bounds__(128)
+k_frame_all(const float* __restrict__ pbw, int C, int D, int H, int W, float* __restrict__ dist, float* __restrict__ cmin,
+            const float* __restrict__ part_pts, int maxlen, const int* __restrict__ perm, const int* __restrict__ cl_off,
+            float4* __restrict__ verts, float4* __restrict__ cl_lo, float4* __restrict__ cl_hi, int nb_prep, int nb_coarse) {
+    const int b = blockIdx.x;
+    if (b < nb_prep) frame_prep_part(pbw, D * H * W, C, dist, b, nb_prep);
+    else if (b < nb_prep + nb_coarse) frame_coarse_part(pbw, C, D, H, W, cmin, b - nb_prep, nb_coarse);
+    else cluster_apply_part(part_pts, maxlen, perm, cl_off, verts, cl_lo, cl_hi, b - nb_prep - nb_coarse, gridDim.x - nb_prep - nb_coarse);
 }
 
 // Exact K=4 nearest vertices of one part for the 32 queries of a warp (one per lane), as a GROUP
