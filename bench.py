@@ -91,32 +91,52 @@ def csrc_hash():
     return h.hexdigest()[:16]
 
 
+_NVML = {}
+
+
+def nvml_handle(index):
+    """NVML initialised ONCE per process (nvmlInit takes ~100 ms: done inside the sampling thread it outlasted a 20-step
+    timed region and the line carried no clock samples)."""
+    if index not in _NVML:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            _NVML[index] = (nv, nv.nvmlDeviceGetHandleByIndex(index))
+        except Exception as e:
+            _NVML[index] = (None, f"nvml_unavailable:{type(e).__name__}")
+    return _NVML[index]
+
+
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons sampled through NVML while the timed region runs."""
+    """SM clock + throttle reasons sampled through NVML while the timed region runs (every 5 ms, first sample at once)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
         self.max_mhz = None
+        self.nv, self.h = nvml_handle(index)
 
     def run(self):
+        nv, h = self.nv, self.h
+        if nv is None:                  # NVML missing: report that rather than fail the bench
+            self.reasons.add(h)
+            return
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
                      "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                      "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-            while not self.stop_flag:
+            while True:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.02)
-        except Exception as e:          # NVML missing: report that rather than fail the bench
+                if self.stop_flag:
+                    break
+                time.sleep(0.005)
+        except Exception as e:
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
     def summary(self):
