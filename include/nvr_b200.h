@@ -134,6 +134,9 @@ typedef struct NvrConfig {
                                           faster: L2 -> SM row delivery is the same ~6.5 TB/s bound) */
 #define NVR_TUNE_WARP_FFMA 128u         /* k_warp with the deformer MLP on the CUDA cores (FFMA2 from broadcast shared-memory loads)
                                           instead of k_warp_tc (tcgen05, fp16-split operands); results agree to ~1e-7 */
+#define NVR_TUNE_ONE_LANE 2048u         /* render calls as one chain of passes on the caller's stream (round-2f behaviour) instead of two
+                                          lanes: two (or more) passes on two streams of the engine, each on half of the workspace, whose
+                                          launch ramps and tails overlap; identical results */
 #define NVR_TUNE_SERIAL 32u            /* one stream, no CUDA graph: every launch of a pass back to back on the caller's stream
                                           (what the per-stage CUDA-event timing of nvr_profile needs; nvr_profile(h, 1) implies it) */
 

@@ -44,7 +44,8 @@ struct NvrEngine {
     float* d_presum = nullptr; size_t presum_cap = 0;     // inference tables: per part [dense rows | hash rows] sums
     size_t presum_off[NVR_PARTS + 1] = {0};
     bool presum_valid = false;
-    int* d_counters_snapshot = nullptr;     // last pass's counters, for nvr_read_counters
+    int* d_counters_snapshot = nullptr;     // last pass's counters (two-lane render: the call's passes summed), for nvr_read_counters
+    bool snapshot_accumulate = false;
     cudaStream_t part_stream[NVR_PARTS] = {nullptr};   // training backward: the five parts' chains run side by side
     cudaEvent_t ev_fork = nullptr, ev_join[NVR_PARTS] = {nullptr};
     long long launches = 0;
@@ -291,7 +292,9 @@ static const size_t WS_PER_POINT = sizeof(int) + sizeof(float4) + NVR_NUM_PARTS 
 extern "C" size_t nvr_workspace_bytes(NvrHandle, int64_t max_points) {
     if (max_points < 1) max_points = 1;
     const size_t pts = ((size_t)max_points + 63) & ~(size_t)63;
-    return WS_HEADER + (pts + 128) * WS_PER_POINT;
+    // + 128: the reserved far-field slots and rounding; + 1024: a two-lane render (render_rays_impl) carves the buffer into two
+    // halves, each with its own header, reserved slots and up to one ray (<= 256 samples) more than half of the points
+    return WS_HEADER + (pts + 128 + 1024) * WS_PER_POINT;
 }
 
 struct Workspace {
@@ -383,7 +386,7 @@ static const float4* far_raws(const NvrEngine* h, const Workspace& w, bool on) {
 static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const float* ray_d, const float* near_,
                     const float* far_, long long n, int n_samples, const float* dirs, int dir_div, cudaStream_t st,
                     float* dbg = nullptr, float* out_x0 = nullptr, float* out_resd = nullptr, bool full_tables = false,
-                    int* rank_of_slot = nullptr) {
+                    int* rank_of_slot = nullptr, bool mlp_prep_done = false) {
     const int sm = h->sm_count;
     const bool dense_a1 = (h->cfg.tune & NVR_TUNE_DENSE_A1) && !dbg && !out_x0;   // measurement variant (a = 1)
     NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
@@ -418,7 +421,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     else
         k_warp<1><<<wg, WARP_THREADS, 0, st>>>(h->fdev, h->def_grid, h->def_mlp, dirs, dir_div, w.counters, w.surv, recs, w.pairs, (int)w.cap, dbg, out_x0, out_resd, rank_of_slot); } }
     const bool tc = h->cfg.mlp_mode >= 1;
-    if (tc) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
+    if (tc && !mlp_prep_done) {   // weights may have changed since the last call (training): repack every pass, 5 small CTAs
         StageTimer t(h, st, NVR_STAGE_MLP);
         launch_mlp_prep(h, st);
         h->launches++;
@@ -488,6 +491,10 @@ static int snapshot_counters(NvrEngine* h, const Workspace& w, cudaStream_t st) 
                                      NVR_CTR_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st));
         h->n_pass_snap++;
     }
+    if (h->snapshot_accumulate) {        // two-lane render: the call's passes add up (both lanes, atomics)
+        k_add_counters<<<1, 32, 0, st>>>(w.counters, h->d_counters_snapshot);
+        NVR_CHECK(h, cudaGetLastError());
+    } else
     NVR_CHECK(h, cudaMemcpyAsync(h->d_counters_snapshot, w.counters, NVR_CTR_WORDS * sizeof(int), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -532,9 +539,51 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
         return fail(h, "nvr_render_rays: null argument");
     Workspace w;
     if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_render_rays: workspace too small or not 256-byte aligned");
-    const long long rays_per_pass = w.pts / n_samples;
+    long long rays_per_pass = w.pts / n_samples;
     if (rays_per_pass < 1) return fail(h, "nvr_render_rays: workspace smaller than one ray");
     cudaStream_t st = (cudaStream_t)stream_;
+    // Two lanes: the call's rays go through the pipeline as (at least) two passes on two streams of the engine, each on its own
+    // half of the workspace, so one pass's kernels fill the SMs the other pass's launch ramps and tails leave idle (a pass is
+    // ~9 dependent launches; at an 8-GPU shard of a 512 x 512 frame ramps + tails were 0.2 of 0.86 ms).  Per-ray results do
+    // not depend on which rays share a pass, so the output is bit-identical to the one-lane render.  Not in the serialised
+    // profiling mode, not for small calls.
+    Workspace lane_w[2];
+    const long long TWO_LANE_MIN_SAMPLES = 1ll << 19;
+    const size_t half_bytes = (ws_bytes / 2) & ~(size_t)255;
+    const bool two = !h->profiling && !(h->cfg.tune & (NVR_TUNE_SERIAL | NVR_TUNE_ONE_LANE | NVR_TUNE_LEVEL_MAJOR)) &&
+                     n_rays * (long long)n_samples >= TWO_LANE_MIN_SAMPLES &&
+                     carve(workspace, half_bytes, lane_w[0]) && carve((char*)workspace + half_bytes, half_bytes, lane_w[1]) &&
+                     lane_w[1].pts / n_samples >= 64;
+    if (two) {
+        rays_per_pass = std::min<long long>(lane_w[1].pts / n_samples, (n_rays + 1) / 2);
+        NVR_CHECK(h, cudaMemsetAsync(h->d_counters_snapshot, 0, NVR_CTR_WORDS * sizeof(int), st));
+        if (h->cfg.mlp_mode >= 1) { launch_mlp_prep(h, st); h->launches++; }        // once per call, before the lanes fork
+        NVR_CHECK(h, cudaEventRecord(h->ev_fork, st));
+        for (int l = 0; l < 2; ++l) NVR_CHECK(h, cudaStreamWaitEvent(h->part_stream[l], h->ev_fork, 0));
+        h->snapshot_accumulate = true;
+        int rc = 0, pass = 0;
+        for (long long r = 0; r < n_rays && !rc; r += rays_per_pass, ++pass) {
+            const Workspace& lw = lane_w[pass & 1];
+            cudaStream_t ls = h->part_stream[pass & 1];
+            const long long nr = std::min<long long>(rays_per_pass, n_rays - r);
+            rc = run_pass(h, lw, ray_o + r * 3, ray_d + r * 3, near_ + r, far_ + r, nr * n_samples, n_samples, ray_d + r * 3, n_samples, ls,
+                          nullptr, nullptr, nullptr, false, nullptr, true);
+            if (rc) break;
+            k_resolve_rays<<<grid_for(nr, 8, h->sm_count * 8), 256, 0, ls>>>(lw.surv_of_sample, lw.raws, far_raws(h, lw, far_collapse(h, nullptr, nullptr)), nr, n_samples,
+                                                                           rgb_map ? rgb_map + r * 3 : nullptr, acc_map ? acc_map + r : nullptr,
+                                                                           raw ? (float4*)raw + r * n_samples : nullptr, fo, r);
+            if (cudaGetLastError() != cudaSuccess) { h->err = "k_resolve_rays launch failed"; rc = 2; break; }
+            h->launches++;
+            rc = snapshot_counters(h, lw, ls);
+        }
+        h->snapshot_accumulate = false;
+        for (int l = 0; l < 2; ++l) {                 // join even after an error: the caller's stream must not run ahead of the lanes
+            cudaEventRecord(h->ev_join[l], h->part_stream[l]);
+            cudaStreamWaitEvent(st, h->ev_join[l], 0);
+        }
+        h->last_points = n_rays * (long long)n_samples;
+        return rc;
+    }
     for (long long r = 0; r < n_rays; r += rays_per_pass) {
         const long long nr = std::min<long long>(rays_per_pass, n_rays - r);
         const long long m = nr * n_samples;

@@ -57,21 +57,26 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.zero_grad_in_step = bool(zero_grad_in_step)   # clear .grad in the same pass (keeps the buffers)
 
-    @torch.no_grad()
-    def step(self, closure=None):
-        loss = None
-        if closure is not None:
-            with torch.enable_grad():
-                loss = closure()
-        # one NvrAdamTensor per parameter with a gradient, grouped by (beta1, beta2, eps).  The ctypes arrays are cached between
-        # steps and only re-built when a pointer moved (a new gradient buffer, a re-loaded state): per step the host then just
-        # bumps `step` / `lr` in place instead of constructing 67 structs
-        entries, touched = [], []
-        device = None
+    # ---- per-step host work ------------------------------------------------------------------------
+    # A step of the reference's optimizer touches 67 tensors.  Walking them the obvious way (a CPU tensor `step += 1` and
+    # `int(step)` per tensor, 67 ctypes structs rebuilt, a 335-pointer cache key) cost 0.55 ms of host time per step, all of
+    # it on the training step's critical path (the Adam launch waits for it).  The plan below is built once and revalidated
+    # per step with two pointer reads per tensor; `step` is bumped through a numpy view of the state's own 0-d tensor.
+    class _Entry:
+        __slots__ = ("p", "group", "st", "m", "v", "step_t", "step_np", "pptr", "gptr", "arr", "j", "lr", "wd", "hyper")
+
+    def _step_view(self, st):
+        t = st["step"]
+        try:
+            return t, (t.numpy() if (t.device.type == "cpu" and t.dtype == torch.float32 and t.dim() == 0) else None)
+        except Exception:
+            return t, None
+
+    def _build_plan(self):
+        entries, device = [], None
         for group in self.param_groups:
             if group.get("amsgrad") or group.get("maximize") or group.get("decoupled_weight_decay"):
                 raise RuntimeError("FusedAdam implements plain Adam only (amsgrad / maximize / AdamW are not on the reference's path)")
-            hyper = (float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]))
             for p in group["params"]:
                 g = p.grad
                 if g is None:
@@ -89,39 +94,88 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                entries.append((hyper, p, g, st, float(group["lr"]), float(group["weight_decay"])))
-                touched += [p, st["exp_avg"], st["exp_avg_sq"]] + ([g] if self.zero_grad_in_step else [])
-        if device is None:
+                e = FusedAdam._Entry()
+                e.p, e.group, e.st, e.m, e.v = p, group, st, st["exp_avg"], st["exp_avg_sq"]
+                e.step_t, e.step_np = self._step_view(st)
+                e.pptr, e.gptr = p.data_ptr(), g.data_ptr()
+                e.lr = e.wd = None
+                entries.append(e)
+        by_hyper: Dict[tuple, List] = {}
+        for e in entries:
+            e.hyper = (float(e.group["betas"][0]), float(e.group["betas"][1]), float(e.group["eps"]))
+            by_hyper.setdefault(e.hyper, []).append(e)
+        arrays = []
+        for hyper, es in by_hyper.items():
+            arr = (cabi.NvrAdamTensor * len(es))()
+            for j, e in enumerate(es):
+                e.arr, e.j = arr, j
+                arr[j].param, arr[j].grad = e.pptr, e.gptr
+                arr[j].exp_avg, arr[j].exp_avg_sq, arr[j].numel = e.m.data_ptr(), e.v.data_ptr(), e.p.numel()
+            arrays.append((hyper, arr, len(es)))
+        n_params = sum(len(g["params"]) for g in self.param_groups)
+        versioned = [t for e in entries for t in (e.p, e.m, e.v)]
+        # (no reference to the gradient tensors is kept: zero_grad(set_to_none=True) must be able to free them)
+        return {"entries": entries, "arrays": arrays, "device": device, "n_params": n_params, "versioned": versioned}
+
+    def _plan_valid(self, plan) -> bool:
+        n = 0
+        for group in self.param_groups:
+            n += len(group["params"])
+        if n != plan["n_params"]:
+            return False
+        seen = 0
+        for e in plan["entries"]:
+            g = e.p.grad
+            st = e.st
+            b = e.group["betas"]
+            if (b[0], b[1], e.group["eps"]) != e.hyper:
+                return False
+            if (g is None or g.data_ptr() != e.gptr or e.p.data_ptr() != e.pptr or st.get("exp_avg") is not e.m
+                    or st.get("exp_avg_sq") is not e.v or st.get("step") is not e.step_t or self.state.get(e.p) is not st):
+                return False
+            seen += 1
+        if seen != n:                    # a parameter without a gradient last time may have one now
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.grad is not None:
+                        seen -= 1
+            return seen == 0
+        return True
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        plan = getattr(self, "_plan", None)
+        if plan is None or not self._plan_valid(plan):
+            plan = self._plan = self._build_plan()
+        if plan["device"] is None:
             return loss
-        key = tuple((e[0], e[1].data_ptr(), e[2].data_ptr(), e[3]["exp_avg"].data_ptr(), e[3]["exp_avg_sq"].data_ptr(), e[1].numel())
-                    for e in entries)
-        cache = getattr(self, "_pack", None)
-        if cache is None or cache["key"] != key:
-            by_hyper: Dict[tuple, List[int]] = {}
-            for i, e in enumerate(entries):
-                by_hyper.setdefault(e[0], []).append(i)
-            arrays = []
-            for hyper, idxs in by_hyper.items():
-                arr = (cabi.NvrAdamTensor * len(idxs))()
-                for j, i in enumerate(idxs):
-                    _, p, g, st, _, _ = entries[i]
-                    arr[j].param, arr[j].grad = p.data_ptr(), g.data_ptr()
-                    arr[j].exp_avg, arr[j].exp_avg_sq, arr[j].numel = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
-                arrays.append((hyper, idxs, arr))
-            cache = self._pack = {"key": key, "arrays": arrays}
+        for e in plan["entries"]:
+            if e.step_np is not None:
+                e.step_np[()] += 1.0
+                cnt = int(e.step_np)
+            else:                        # a step tensor that is not a 0-d fp32 CPU tensor (e.g. a capturable checkpoint)
+                e.step_t += 1
+                cnt = int(e.step_t)
+            a = e.arr[e.j]
+            a.step = cnt
+            lr, wd = e.group["lr"], e.group["weight_decay"]
+            if lr != e.lr:
+                a.lr = e.lr = float(lr)
+            if wd != e.wd:
+                a.weight_decay = e.wd = float(wd)
+        device = plan["device"]
         lib, h = aux_handle(device)
         stream = torch.cuda.current_stream(device).cuda_stream
         with torch.cuda.device(device):
-            for (beta1, beta2, eps), idxs, arr in cache["arrays"]:
-                for j, i in enumerate(idxs):
-                    _, _, _, st, lr, wd = entries[i]
-                    arr[j].step, arr[j].lr, arr[j].weight_decay = int(st["step"]), lr, wd
-                check(lib, h, lib.nvr_adam_step(h, arr, len(idxs), beta1, beta2, eps, int(self.zero_grad_in_step), stream),
-                      "nvr_adam_step")
+            for (beta1, beta2, eps), arr, n in plan["arrays"]:
+                check(lib, h, lib.nvr_adam_step(h, arr, n, beta1, beta2, eps, int(self.zero_grad_in_step), stream), "nvr_adam_step")
         # the library wrote through raw pointers: tell autograd / anything keyed on tensor versions (the engine's
         # pre-summed inference tables) that these tensors changed in place, as torch.optim.Adam's in-place ops would
-        torch.autograd.graph.increment_version(touched)
+        torch.autograd.graph.increment_version(plan["versioned"] + ([e.p.grad for e in plan["entries"]] if self.zero_grad_in_step else []))
         return loss
 
 
