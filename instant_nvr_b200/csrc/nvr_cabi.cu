@@ -390,10 +390,13 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     const int sm = h->sm_count;
     const bool dense_a1 = (h->cfg.tune & NVR_TUNE_DENSE_A1) && !dbg && !out_x0;   // measurement variant (a = 1)
     NVR_CHECK(h, cudaMemsetAsync(w.counters, 0, NVR_CTR_WORDS * sizeof(int), st));
+    // KNN unit descriptors (k_cull -> k_knn) borrow the head of the pair lists, which k_warp only writes after k_knn is done:
+    // at most one unit per 32 survivors + 4 per 2048-position span, 8 B each, against 160 B of pair records per sample
+    int2* units = (int2*)w.pairs;
     { StageTimer t(h, st, NVR_STAGE_CULL);
     NVR_CHECK(h, cudaMemsetAsync(w.surv_of_sample, 0xFF, (size_t)n * sizeof(int), st));   // -1 = culled; k_cull fills in the survivors
     k_cull<<<grid_for(n, 256 * CULL_T, sm * 8), 256, 0, st>>>(h->fdev, pts, ray_d, near_, far_, n, n_samples, h->cfg.smpl_thresh,
-                                                      w.counters, w.surv_of_sample, w.surv, dense_a1 ? 1 : 0); }
+                                                      w.counters, w.surv_of_sample, w.surv, dense_a1 ? 1 : 0, units); }
     if (rank_of_slot) {      // training: survivors' positions in ascending sample order (the order the reference returns them in)
         k_rank_slots<<<1, 1024, 0, st>>>(w.surv_of_sample, n, rank_of_slot);
         h->launches++;
@@ -403,11 +406,11 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     const int far_slot = far_collapse(h, dbg, out_x0) ? (int)w.cap - 1 : -1;
     { StageTimer t(h, st, NVR_STAGE_KNN);
     if (dense_a1)
-        k_knn<4, true><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, nullptr, -1);
+        k_knn<4, true><<<grid_for(n, 256, sm * 8), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, nullptr, -1, units);
     else if (h->cfg.tune & NVR_TUNE_KNN_OCC5)   // <= 48 registers: 5 CTAs (40 warps) per SM instead of 4
-        k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot);
+        k_knn<5><<<grid_for(n, 256, sm * 10), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot, units);
     else
-        k_knn<4><<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot); }   // work-counter loop: one wave of resident CTAs
+        k_knn<4><<<grid_for(n, 256, sm * 4), 256, 0, st>>>(h->fdev, h->cfg.smpl_thresh, w.counters, w.surv, recs, (int)w.cap, w.raws, dbg, far_slot, units); }   // work-counter loop: one wave of resident CTAs
     { StageTimer t(h, st, NVR_STAGE_WARP);
     if (!(h->cfg.tune & (NVR_TUNE_WARP_FFMA | NVR_TUNE_WARP_OCC4))) {
         // default: deformer MLP on tcgen05, one 128-pair tile per CTA iteration (nvr_warp_tc.cuh)
@@ -877,8 +880,13 @@ extern "C" int nvr_train_forward(NvrHandle h, const float* wpts, const float* vi
 static size_t train_scratch_bytes(long long cap) {
     return 256 + (size_t)cap * NVR_NUM_PARTS * (sizeof(GradRec) + (NVR_EMB_STRIDE + 9) * sizeof(float));
 }
-// sized for the stride of a workspace of nvr_workspace_bytes(n): carve() gives cap = round_up(n, 64) + 64
-extern "C" size_t nvr_train_scratch_bytes(NvrHandle, int64_t n) { return train_scratch_bytes((((n < 1 ? 1 : n) + 63) & ~63ll) + 64); }
+// sized for the stride carve() gives a workspace of nvr_workspace_bytes(n) (the same arithmetic, so the two cannot drift apart)
+extern "C" size_t nvr_train_scratch_bytes(NvrHandle h, int64_t n) {
+    const size_t bytes = nvr_workspace_bytes(h, n);
+    long long cap = (long long)((bytes - WS_HEADER) / WS_PER_POINT) - 64;
+    cap = std::min<long long>(cap & ~63ll, 1ll << 30);
+    return train_scratch_bytes(cap);
+}
 
 static PartMlpGrad mlp_grad(const NvrPart& g, int n_rgb) {
     PartMlpGrad o;

@@ -27,6 +27,7 @@
 #define NVR_CTR_FAR 6              // [6..10] flagged pairs answered by the part's shared far-field pair
 #define NVR_CTR_WORK 11             // k_knn's dynamic work-unit counter
 #define NVR_CTR_EMBED_WORK 12       // [12..16] k_embed_parts' work-unit counters, one per part
+#define NVR_CTR_UNITS 17            // k_cull's count of KNN unit descriptors (groups of <= 32 neighbouring survivors)
 #define NVR_CTR_WORDS 32
 // Far-field pairs.  A part farther than ~0.73 m from a sample still gets flagged (its Gaussian weights sum to far less
 // than the 1e-8 in the normalisation, so pdist -> 0 < smpl_thresh: DESIGN.md section 1).  Once sum(w) < NVR_FAR_WSUM the
@@ -384,8 +385,14 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
 __global__ void __launch_bounds__(256, 4)
 k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray_d,
        const float* __restrict__ near_, const float* __restrict__ far_, long long n, int n_samples,
-       float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv, int keep_all) {
+       float thresh, int* __restrict__ counters, int* __restrict__ surv_of_sample, float4* __restrict__ surv, int keep_all,
+       int2* __restrict__ units) {
     // keep_all (NVR_TUNE_DENSE_A1, measurement variant): every valid sample survives, whatever its distance
+    // units: KNN work units (first survivor slot, 1..32 survivors).  A unit never crosses a span -- two spans are appended in
+    // completion order and can lie anywhere in the frame -- nor an empty warp segment inside a span (8 depth steps = the gap
+    // between a ray group's entry and exit shells), so the 32 queries a k_knn warp searches for together are neighbours.
+    // With units cut every 32 slots of the survivor list, ~2 in 5 of them straddled two regions tens of cm apart and the
+    // group search pruned against a query box spanning both.
     __shared__ float4 s_surv[CULL_SPAN];
     __shared__ int warp_cnt[8];
     __shared__ int s_base;
@@ -464,7 +471,30 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
         int off = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; off += w < wid ? c : 0; total += c; }
-        if (threadIdx.x == 0) s_base = total ? atomicAdd(&counters[NVR_CTR_SURV], total) : 0;
+        if (threadIdx.x == 0) {
+            s_base = total ? atomicAdd(&counters[NVR_CTR_SURV], total) : 0;
+            if (total && units) {                                  // runs of consecutive non-empty warp segments -> units of <= 32
+                int nu = 0, runlen = 0;
+#pragma unroll
+                for (int w = 0; w <= 8; ++w) {
+                    const int c = w < 8 ? warp_cnt[w] : 0;
+                    if (c) runlen += c;
+                    else { nu += (runlen + 31) >> 5; runlen = 0; }
+                }
+                int u = atomicAdd(&counters[NVR_CTR_UNITS], nu);
+                int start = s_base;
+                runlen = 0;
+#pragma unroll
+                for (int w = 0; w <= 8; ++w) {
+                    const int c = w < 8 ? warp_cnt[w] : 0;
+                    if (c) runlen += c;
+                    else {
+                        for (int done = 0; done < runlen; done += 32) units[u++] = make_int2(start + done, min(32, runlen - done));
+                        start += runlen; runlen = 0;
+                    }
+                }
+            }
+        }
         __syncthreads();
         const int gbase = s_base + off;
         for (int x = lane; x < run; x += 32) {                    // each warp appends its own segment
@@ -526,7 +556,8 @@ struct __align__(16) KnnRec {      // a flagged (sample, part) pair before the w
 template <int MINB, bool DENSE = false>
 __global__ void __launch_bounds__(256, MINB)
 k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict__ surv,
-      KnnRec* __restrict__ recs, int cap, float4* __restrict__ raws, float* __restrict__ dbg, int far_slot) {
+      KnnRec* __restrict__ recs, int cap, float4* __restrict__ raws, float* __restrict__ dbg, int far_slot,
+      const int2* __restrict__ units) {
     // dbg (optional, per SAMPLE): [n][5][8] = flag, x, y, z, vx, vy, vz, pdist -- per-stage parity tests
     // far_slot >= 0: survivor slot reserved for the shared far-field pairs (NVR_FAR_WSUM); -1 = evaluate every pair
     const int n_surv = counters[NVR_CTR_SURV];
@@ -547,7 +578,7 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
     // Units are numbered part-major, body first: the body part has the most clusters and the most survivors next to it, the
     // arms are far-field / certainly unflagged for most of the frame, so the expensive searches are handed out first and the
     // launch ends on cheap units (ncu on an 8-GPU shard: SM active cycles avg / max 0.71 with the parts interleaved).
-    const int n_groups = (n_surv + 31) / 32;
+    const int n_groups = counters[NVR_CTR_UNITS];                 // k_cull's unit descriptors (groups of neighbouring survivors)
     const int n_units = n_groups * (DENSE ? 1 : NVR_PARTS);
     while (true) {
         int unit = 0;
@@ -555,8 +586,9 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= n_units) break;
         const int unit_part = DENSE ? 0 : unit / n_groups;
-        const int s = (DENSE ? unit : unit - unit_part * n_groups) * 32 + lane;
-        const bool live = s < n_surv;
+        const int2 ud = units[DENSE ? unit : unit - unit_part * n_groups];
+        const int s = ud.x + lane;
+        const bool live = lane < ud.y;
         float p[3] = {0.f, 0.f, 0.f};
         int sample = 0;
         if (live) {
