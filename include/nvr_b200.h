@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NVR_ABI_VERSION 9
+#define NVR_ABI_VERSION 10
 #define NVR_MAX_LEVELS 16
 #define NVR_NUM_PARTS 5    /* body, leg, head, larm, rarm -- lib/utils/blend_utils.py:17 */
 #define NVR_NUM_JOINTS 24
@@ -140,7 +140,7 @@ typedef struct NvrConfig {
 #define NVR_TUNE_SERIAL 32u            /* one stream, no CUDA graph: every launch of a pass back to back on the caller's stream
                                           (what the per-stage CUDA-event timing of nvr_profile needs; nvr_profile(h, 1) implies it) */
 
-/* Device-side work counters of the most recent pass (diagnostics / benchmark accounting). */
+/* Device-side work counters of the most recent call's passes (diagnostics / benchmark accounting). */
 typedef struct NvrCounters {
     int64_t n_points;              /* samples submitted */
     int64_t n_survivors;           /* samples with pnorm < smpl_thresh */
@@ -148,6 +148,8 @@ typedef struct NvrCounters {
     int64_t n_far_pairs[NVR_NUM_PARTS]; /* flagged pairs answered by the shared far-field pair (NVR_TUNE_NO_FAR_COLLAPSE: 0);
                                       flagged pairs of the reference = n_pairs + n_far_pairs - (n_far_pairs or collapse on ? 1 : 0) */
     int64_t kernel_launches;       /* kernels this handle has launched since creation */
+    int64_t n_passes;              /* passes the most recent call ran (a two-lane render: >= 2; the counters above are their
+                                      sums, so n_pairs holds one shared far-field pair per part PER PASS) */
 } NvrCounters;
 
 int nvr_abi_version(void);

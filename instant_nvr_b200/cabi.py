@@ -12,7 +12,7 @@ from typing import Optional
 
 MAX_LEVELS = 16
 NUM_PARTS = 5
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnvr_b200.so")
@@ -64,7 +64,7 @@ class NvrConfig(C.Structure):
 
 class NvrCounters(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_survivors", C.c_int64), ("n_pairs", C.c_int64 * NUM_PARTS),
-                ("n_far_pairs", C.c_int64 * NUM_PARTS), ("kernel_launches", C.c_int64)]
+                ("n_far_pairs", C.c_int64 * NUM_PARTS), ("kernel_launches", C.c_int64), ("n_passes", C.c_int64)]
 
 
 class NvrStageProfile(C.Structure):

@@ -50,6 +50,7 @@ struct NvrEngine {
     cudaEvent_t ev_fork = nullptr, ev_join[NVR_PARTS] = {nullptr};
     long long launches = 0;
     long long last_points = 0;
+    long long last_passes = 1;
     // multi-GPU frame assembly (nvr_frame.cuh): the local buffer [flags | slot 0 | slot 1] and the peers' mappings
     struct PeerFrame {
         void* local = nullptr; void* peer[NVR_MAX_RANKS] = {nullptr};
@@ -485,6 +486,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     NVR_CHECK(h, cudaGetLastError());
     h->launches += 3 + 2 * NVR_NUM_PARTS;
     h->last_points = n;
+    h->last_passes = 1;
     return 0;
 }
 
@@ -533,9 +535,13 @@ extern "C" int nvr_query_points(NvrHandle h, const float* wpts, const float* vie
     return 0;
 }
 
+// nvr_render_rays_host: the pinned host buffers behind the device arrays.  A two-lane render copies each pass's rays in and its
+// pixels out on the pass's own stream, so the second lane's H2D and the first lane's D2H run under the other lane's kernels.
+struct HostIO { const float* ray_o; const float* ray_d; const float* near_; const float* far_; float* rgb; float* acc; };
+
 static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d, const float* near_, const float* far_,
                             int64_t n_rays, int32_t n_samples, float* rgb_map, float* acc_map, float* raw,
-                            void* workspace, size_t ws_bytes, void* stream_, const FrameOut& fo) {
+                            void* workspace, size_t ws_bytes, void* stream_, const FrameOut& fo, const HostIO* hio = nullptr) {
     if (int rc = ready(h, "nvr_render_rays")) return rc;
     if (n_rays < 0 || n_samples < 1) return fail(h, "nvr_render_rays: bad n_rays / n_samples");
     if (n_rays > 0 && (!ray_o || !ray_d || !near_ || !far_ || ((!rgb_map || !acc_map) && fo.world == 0) || (!rgb_map != !acc_map)))
@@ -569,6 +575,14 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
             const Workspace& lw = lane_w[pass & 1];
             cudaStream_t ls = h->part_stream[pass & 1];
             const long long nr = std::min<long long>(rays_per_pass, n_rays - r);
+            if (hio) {
+                cudaMemcpyAsync((float*)ray_o + r * 3, hio->ray_o + r * 3, nr * 3 * sizeof(float), cudaMemcpyHostToDevice, ls);
+                cudaMemcpyAsync((float*)ray_d + r * 3, hio->ray_d + r * 3, nr * 3 * sizeof(float), cudaMemcpyHostToDevice, ls);
+                cudaMemcpyAsync((float*)near_ + r, hio->near_ + r, nr * sizeof(float), cudaMemcpyHostToDevice, ls);
+                if (cudaMemcpyAsync((float*)far_ + r, hio->far_ + r, nr * sizeof(float), cudaMemcpyHostToDevice, ls) != cudaSuccess) {
+                    h->err = std::string("nvr_render_rays_host: H2D copy: ") + cudaGetErrorString(cudaGetLastError()); rc = 2; break;
+                }
+            }
             rc = run_pass(h, lw, ray_o + r * 3, ray_d + r * 3, near_ + r, far_ + r, nr * n_samples, n_samples, ray_d + r * 3, n_samples, ls,
                           nullptr, nullptr, nullptr, false, nullptr, true);
             if (rc) break;
@@ -577,6 +591,12 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
                                                                            raw ? (float4*)raw + r * n_samples : nullptr, fo, r);
             if (cudaGetLastError() != cudaSuccess) { h->err = "k_resolve_rays launch failed"; rc = 2; break; }
             h->launches++;
+            if (hio) {
+                cudaMemcpyAsync(hio->rgb + r * 3, rgb_map + r * 3, nr * 3 * sizeof(float), cudaMemcpyDeviceToHost, ls);
+                if (cudaMemcpyAsync(hio->acc + r, acc_map + r, nr * sizeof(float), cudaMemcpyDeviceToHost, ls) != cudaSuccess) {
+                    h->err = std::string("nvr_render_rays_host: D2H copy: ") + cudaGetErrorString(cudaGetLastError()); rc = 2; break;
+                }
+            }
             rc = snapshot_counters(h, lw, ls);
         }
         h->snapshot_accumulate = false;
@@ -585,7 +605,14 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
             cudaStreamWaitEvent(st, h->ev_join[l], 0);
         }
         h->last_points = n_rays * (long long)n_samples;
+        h->last_passes = pass;
         return rc;
+    }
+    if (hio) {
+        NVR_CHECK(h, cudaMemcpyAsync((float*)ray_o, hio->ray_o, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        NVR_CHECK(h, cudaMemcpyAsync((float*)ray_d, hio->ray_d, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+        NVR_CHECK(h, cudaMemcpyAsync((float*)near_, hio->near_, n_rays * sizeof(float), cudaMemcpyHostToDevice, st));
+        NVR_CHECK(h, cudaMemcpyAsync((float*)far_, hio->far_, n_rays * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     for (long long r = 0; r < n_rays; r += rays_per_pass) {
         const long long nr = std::min<long long>(rays_per_pass, n_rays - r);
@@ -599,6 +626,10 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
         NVR_CHECK(h, cudaGetLastError());
         h->launches++;
         if (int rc = snapshot_counters(h, w, st)) return rc;
+    }
+    if (hio) {
+        NVR_CHECK(h, cudaMemcpyAsync(hio->rgb, rgb_map, n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        NVR_CHECK(h, cudaMemcpyAsync(hio->acc, acc_map, n_rays * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     return 0;
 }
@@ -736,14 +767,11 @@ extern "C" int nvr_render_rays_host(NvrHandle h, const float* ray_o_host, const 
     float* d = (float*)dev_io;                      // [o 3n | d 3n | near n | far n | rgb 3n | acc n] = 12n floats
     float *d_o = d, *d_d = d + 3 * n_rays, *d_n = d + 6 * n_rays, *d_f = d + 7 * n_rays, *d_rgb = d + 8 * n_rays,
           *d_acc = d + 11 * n_rays;
-    NVR_CHECK(h, cudaMemcpyAsync(d_o, ray_o_host, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    NVR_CHECK(h, cudaMemcpyAsync(d_d, ray_d_host, n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    NVR_CHECK(h, cudaMemcpyAsync(d_n, near_host, n_rays * sizeof(float), cudaMemcpyHostToDevice, st));
-    NVR_CHECK(h, cudaMemcpyAsync(d_f, far_host, n_rays * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (int rc = nvr_render_rays(h, d_o, d_d, d_n, d_f, n_rays, n_samples, d_rgb, d_acc, nullptr, workspace, ws_bytes, stream_))
+    const HostIO hio{ray_o_host, ray_d_host, near_host, far_host, rgb_map_host, acc_map_host};
+    FrameOut none;
+    memset(&none, 0, sizeof(none));
+    if (int rc = render_rays_impl(h, d_o, d_d, d_n, d_f, n_rays, n_samples, d_rgb, d_acc, nullptr, workspace, ws_bytes, stream_, none, &hio))
         return rc;
-    NVR_CHECK(h, cudaMemcpyAsync(rgb_map_host, d_rgb, n_rays * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    NVR_CHECK(h, cudaMemcpyAsync(acc_map_host, d_acc, n_rays * sizeof(float), cudaMemcpyDeviceToHost, st));
     NVR_CHECK(h, cudaStreamSynchronize(st));
     return 0;
 }
@@ -1293,5 +1321,6 @@ extern "C" int nvr_read_counters(NvrHandle h, NvrCounters* out, void* stream_) {
     out->n_survivors = host[NVR_CTR_SURV];
     for (int p = 0; p < NVR_NUM_PARTS; ++p) { out->n_pairs[p] = host[NVR_CTR_PAIR + p]; out->n_far_pairs[p] = host[NVR_CTR_FAR + p]; }
     out->kernel_launches = h->launches;
+    out->n_passes = h->last_passes;
     return 0;
 }

@@ -424,4 +424,4 @@ class Engine:
         c = cabi.NvrCounters()
         self._check(self.lib.nvr_read_counters(self._h, C.byref(c), _stream_ptr(self.device)), "nvr_read_counters")
         return {"n_points": c.n_points, "n_survivors": c.n_survivors, "n_pairs": list(c.n_pairs),
-                "n_far_pairs": list(c.n_far_pairs), "kernel_launches": c.kernel_launches}
+                "n_far_pairs": list(c.n_far_pairs), "kernel_launches": c.kernel_launches, "n_passes": c.n_passes}

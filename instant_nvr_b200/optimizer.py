@@ -63,7 +63,7 @@ class FusedAdam(torch.optim.Optimizer):
     # it on the training step's critical path (the Adam launch waits for it).  The plan below is built once and revalidated
     # per step with two pointer reads per tensor; `step` is bumped through a numpy view of the state's own 0-d tensor.
     class _Entry:
-        __slots__ = ("p", "group", "st", "m", "v", "step_t", "step_np", "pptr", "gptr", "arr", "j", "lr", "wd", "hyper")
+        __slots__ = ("p", "group", "st", "m", "v", "step_t", "step_np", "pptr", "gptr", "a", "lr", "wd", "hyper")
 
     def _step_view(self, st):
         t = st["step"]
@@ -108,7 +108,7 @@ class FusedAdam(torch.optim.Optimizer):
         for hyper, es in by_hyper.items():
             arr = (cabi.NvrAdamTensor * len(es))()
             for j, e in enumerate(es):
-                e.arr, e.j = arr, j
+                e.a = arr[j]                     # a view of the array element: field writes go straight into `arr`
                 arr[j].param, arr[j].grad = e.pptr, e.gptr
                 arr[j].exp_avg, arr[j].exp_avg_sq, arr[j].numel = e.m.data_ptr(), e.v.data_ptr(), e.p.numel()
             arrays.append((hyper, arr, len(es)))
@@ -151,6 +151,7 @@ class FusedAdam(torch.optim.Optimizer):
         plan = getattr(self, "_plan", None)
         if plan is None or not self._plan_valid(plan):
             plan = self._plan = self._build_plan()
+            self.plan_builds = getattr(self, "plan_builds", 0) + 1
         if plan["device"] is None:
             return loss
         for e in plan["entries"]:
@@ -160,7 +161,7 @@ class FusedAdam(torch.optim.Optimizer):
             else:                        # a step tensor that is not a 0-d fp32 CPU tensor (e.g. a capturable checkpoint)
                 e.step_t += 1
                 cnt = int(e.step_t)
-            a = e.arr[e.j]
+            a = e.a
             a.step = cnt
             lr, wd = e.group["lr"], e.group["weight_decay"]
             if lr != e.lr:

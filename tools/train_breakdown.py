@@ -72,7 +72,13 @@ torch.cuda.synchronize(); e0 = ev()
 for _ in range(N):
     opt.zero_grad(set_to_none=True); loss_of(r.render(dict(batch))).backward(); opt.step()
 e1 = ev(); torch.cuda.synchronize()
-print("back-to-back ms per step: %.3f" % (e0.elapsed_time(e1) / N))
+print("back-to-back ms per step: %.3f" % (e0.elapsed_time(e1) / N), " optimizer plan builds so far:", getattr(opt, "plan_builds", None))
+for _ in range(2):
+    torch.cuda.synchronize(); e0 = ev()
+    for _ in range(N):
+        opt.zero_grad(set_to_none=True); loss_of(r.render(dict(batch))).backward(); opt.step()
+    e1 = ev(); torch.cuda.synchronize()
+    print("back-to-back ms per step (again): %.3f" % (e0.elapsed_time(e1) / N), " plan builds:", getattr(opt, "plan_builds", None))
 
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
