@@ -51,6 +51,7 @@ struct NvrEngine {
     long long launches = 0;
     long long last_points = 0;
     long long last_passes = 1;
+    int last_lanes = 1;                     // 2: the most recent call carved its workspace into two halves (two-lane render)
     // multi-GPU frame assembly (nvr_frame.cuh): the local buffer [flags | slot 0 | slot 1] and the peers' mappings
     struct PeerFrame {
         void* local = nullptr; void* peer[NVR_MAX_RANKS] = {nullptr};
@@ -487,6 +488,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     h->launches += 3 + 2 * NVR_NUM_PARTS;
     h->last_points = n;
     h->last_passes = 1;
+    h->last_lanes = 1;
     return 0;
 }
 
@@ -606,6 +608,7 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
         }
         h->last_points = n_rays * (long long)n_samples;
         h->last_passes = pass;
+        h->last_lanes = 2;
         return rc;
     }
     if (hio) {
@@ -1247,8 +1250,15 @@ extern "C" int nvr_smpl_bweights(NvrHandle h, const void* workspace, int32_t n_v
 extern "C" int nvr_gather_footprint(NvrHandle h, void* workspace, size_t ws_bytes, int64_t* unique_sectors_host, void* stream_) {
     if (int rc = ready(h, "nvr_gather_footprint")) return rc;
     if (!unique_sectors_host) return fail(h, "nvr_gather_footprint: null argument");
-    Workspace w;
-    if (!carve(workspace, ws_bytes, w)) return fail(h, "nvr_gather_footprint: not a pass workspace");
+    // the layout the most recent call used: one workspace, or the two halves of a two-lane render (one pass each; the union
+    // of both halves' pair lists is the frame's footprint)
+    Workspace lw[2];
+    const int lanes = h->last_lanes;
+    const size_t half_bytes = (ws_bytes / 2) & ~(size_t)255;
+    if (lanes == 2 ? !(carve(workspace, half_bytes, lw[0]) && carve((char*)workspace + half_bytes, half_bytes, lw[1]))
+                   : !carve(workspace, ws_bytes, lw[0]))
+        return fail(h, "nvr_gather_footprint: not a pass workspace");
+    if (h->last_passes > lanes) return fail(h, "nvr_gather_footprint: the last call ran more than one pass per lane");
     cudaStream_t st = (cudaStream_t)stream_;
     size_t max_words = 0;
     for (int p = 0; p < NVR_NUM_PARTS; ++p) {
@@ -1264,8 +1274,11 @@ extern "C" int nvr_gather_footprint(NvrHandle h, void* workspace, size_t ws_byte
         const NvrGrid& g = h->params.part[p].grid;
         const size_t words = (size_t)((2 * (dense_rows(g) + hash_rows(g)) + 31) / 32);
         cudaMemsetAsync(bitmap, 0, words * sizeof(unsigned int), st);
-        k_embed_footprint<<<h->sm_count * 8, 256, 0, st>>>(h->part_grid[p], (const float*)(w.pairs + (long long)p * w.cap), 8,
-                                                           w.counters + NVR_CTR_PAIR + p, bitmap, 2ull * (unsigned long long)dense_rows(g));
+        for (int l = 0; l < lanes; ++l) {
+            const Workspace& w = lw[l];
+            k_embed_footprint<<<h->sm_count * 8, 256, 0, st>>>(h->part_grid[p], (const float*)(w.pairs + (long long)p * w.cap), 8,
+                                                               w.counters + NVR_CTR_PAIR + p, bitmap, 2ull * (unsigned long long)dense_rows(g));
+        }
         k_popcount_words<<<h->sm_count * 4, 256, 0, st>>>(bitmap, (long long)words, d_out + p);
     }
     unsigned long long host[NVR_NUM_PARTS];

@@ -407,6 +407,25 @@ def test_full_size_properties_c2(full):
     diag("c2_render", seconds=dt, ray_samples=512 * 512 * S, **c)
     assert torch.isfinite(rgb).all() and torch.isfinite(acc).all()
     assert acc.min() >= 0 and acc.max() <= 1 + 1e-5 and rgb.min() >= 0 and rgb.max() <= 1 + 1e-5
+    # (0) the frame went through the pipeline as two lanes (two passes on two streams, half a workspace each): the one-lane
+    #     render (NVR_TUNE_ONE_LANE) and the host entry point (each lane copies its own rays in and pixels out) give the same bits
+    from instant_nvr_b200.engine import Engine
+    assert c["n_passes"] == 2
+    fp2 = eng.gather_footprint()                              # distinct table sectors over BOTH lanes' pair lists
+    eng1 = Engine(cfg, tune=2048)
+    eng1.bind_params(net)
+    rgb_1, acc_1 = eng1.render_rays(o, d, n, f, S, batch=gb)
+    assert eng1.counters()["n_passes"] == 1
+    assert eng1.gather_footprint() == fp2 and min(fp2) > 0
+    assert torch.equal(rgb_1, rgb) and torch.equal(acc_1, acc)
+    c1 = eng1.counters()
+    assert c1["n_survivors"] == c["n_survivors"] and c1["n_far_pairs"] == c["n_far_pairs"]
+    assert [a - 1 for a in c1["n_pairs"]] == [a - 2 for a in c["n_pairs"]]        # one shared far-field pair per part and pass
+    del eng1
+    host = [t.cpu().contiguous().pin_memory() for t in (o, d, n, f)]
+    rgb_h, acc_h = torch.empty(o.shape[0], 3).pin_memory(), torch.empty(o.shape[0]).pin_memory()
+    eng.render_rays_host(*host, S, rgb_h, acc_h)
+    assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(acc_h, acc.cpu())
     # (1) ray-permutation equivariance: rendering a shuffled subset gives the same pixels (bit-exact:
     #     per-ray results do not depend on neighbours or on compaction order)
     perm = torch.randperm(512 * 512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))[:20000]
