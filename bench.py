@@ -258,7 +258,16 @@ def ncu_traffic(kernel):
     together with whether that capture was taken from the sources this library was built from."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(REPO, "profiles", "*ncu_full_summary.csv")), key=os.path.getmtime)
+    # the capture taken from THIS library's sources first (meta.json carries the hash), then the newest by name (r2h > r2a > r1l:
+    # file times mean nothing after a checkout)
+    def rank(path):
+        meta_path = path.replace(".csv", ".meta.json")
+        try:
+            same = json.load(open(meta_path)).get("csrc_hash") == csrc_hash()
+        except Exception:
+            same = False
+        return (same, os.path.basename(path))
+    files = sorted(glob.glob(os.path.join(REPO, "profiles", "*ncu_full_summary.csv")), key=rank)
     for path in reversed(files):
         try:
             rows = list(csv.reader(open(path)))

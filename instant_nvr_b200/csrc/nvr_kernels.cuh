@@ -372,13 +372,13 @@ __device__ __forceinline__ int knn_part_group(const FrameDev& fr, int part, cons
 // -----------------------------------------------------------------------------------------
 // ray mode  (n_samples > 0): sample i = ray i / n_samples, step i % n_samples; pts = ray_o, aux = ray_d
 // point mode (n_samples == 0): pts = wpts (n,3)
-// Ray mode walks the samples DEPTH-MAJOR inside groups of 32 consecutive rays (position j -> ray 32 g + j % 32, step
-// (j / 32) % S), so the survivor list -- and with it every later kernel's warps -- holds neighbouring pixels at one
-// depth (a few cm across) instead of the entry and exit shells of one ray (tens of cm apart): tighter KNN query
-// boxes, shared neighbour rows and grid cells.  A CTA compacts CULL_T chunks of 256 positions (64 depth steps of one
-// ray group) in shared memory and appends them with ONE atomic, so the runs of neighbouring survivors are hundreds
-// long and the survivor records leave as coalesced 16-byte stores.  Results are per sample and do not depend on the
-// order.
+// Ray mode walks the samples DEPTH-MAJOR inside groups of 32 consecutive rays, in chunks of 16 rays x 2 depth steps
+// (cull_locate, nvr_math.cuh), so the survivor list -- and with it every later kernel's warps -- holds neighbouring
+// pixels at neighbouring depths (a few cm across) instead of the entry and exit shells of one ray (tens of cm apart):
+// tighter KNN query boxes, shared neighbour rows and grid cells.  A CTA compacts CULL_T chunks of 256 positions (64 depth
+// steps of one ray group) in shared memory and appends them with ONE atomic, so the runs of neighbouring survivors are
+// hundreds long and the survivor records leave as coalesced 16-byte stores.  Results are per sample and do not depend on
+// the order.
 #define CULL_T 8
 #define CULL_SPAN (256 * CULL_T)
 // surv_of_sample must be pre-filled with -1 (cudaMemsetAsync 0xFF): only survivors' entries are written here.
@@ -400,7 +400,7 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
     const bool rays = n_samples > 0;
     CullWalk cw;
     cw.S = rays ? n_samples : 1;
-    cw.group = 32u * (unsigned)cw.S;
+    cw.group = cull_group_positions(cw.S);
     cw.n_rays = rays ? n / n_samples : 0;
     const long long n_map = rays ? ((cw.n_rays + 31) / 32) * (long long)cw.group : n;
     __shared__ CullQuick cq;                                      // uniform: one copy per CTA, broadcast reads
@@ -410,7 +410,8 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
     for (long long sbase = (long long)blockIdx.x * CULL_SPAN; sbase < n_map; sbase += (long long)gridDim.x * CULL_SPAN) {
         cw.g0 = sbase / (long long)cw.group;
         cw.w0 = (unsigned)(sbase - cw.g0 * (long long)cw.group);
-        // warp `wid` owns positions [wid * 256, wid * 256 + 256) of the span -- 8 consecutive depth steps of the 32 rays --
+        // warp `wid` owns positions [wid * 256, wid * 256 + 256) of the span -- 8 consecutive depth steps of the 32 rays, as
+        // 4 chunks (16 rays x 2 steps) of one half of the rays and then 4 of the other half --
         // and compacts them into its own 256-record segment of s_surv: no CTA barrier inside the loop
         int run = 0;                                              // survivors of this warp so far (warp-uniform)
         long long r_have = -1;                                    // the ray whose data the registers below hold
@@ -428,7 +429,7 @@ k_cull(FrameDev fr, const float* __restrict__ pts, const float* __restrict__ ray
                 float w[3], c[3];
                 bool culled = false;
                 if (rays) {
-                    if (r != r_have) {                            // a lane keeps its ray for the whole span (32 | 256)
+                    if (r != r_have) {                            // a lane changes ray once per span (the group's other 16 rays)
                         r_have = r;
 #pragma unroll
                         for (int a = 0; a < 3; ++a) { o[a] = pts[r * 3 + a]; d[a] = ray_d[r * 3 + a]; }
@@ -580,11 +581,13 @@ k_knn(FrameDev fr, float thresh, int* __restrict__ counters, float4* __restrict_
     // launch ends on cheap units (ncu on an 8-GPU shard: SM active cycles avg / max 0.71 with the parts interleaved).
     const int n_groups = counters[NVR_CTR_UNITS];                 // k_cull's unit descriptors (groups of neighbouring survivors)
     const int n_units = n_groups * (DENSE ? 1 : NVR_PARTS);
-    while (true) {
-        int unit = 0;
-        if (lane == 0) unit = atomicAdd(&counters[NVR_CTR_WORK], 1);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
+    // the counter fetch for the NEXT unit is issued before this unit is searched, so its round trip (11 % of the stall samples
+    // when it sat at the top of the loop, profiles/r2h_line_stalls_k_knn.txt) runs under the search
+    int unit = 0;
+    if (lane == 0) unit = atomicAdd(&counters[NVR_CTR_WORK], 1);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    for (int next = 0; unit < n_units; unit = __shfl_sync(0xffffffffu, next, 0)) {
+        if (lane == 0) next = atomicAdd(&counters[NVR_CTR_WORK], 1);
         const int unit_part = DENSE ? 0 : unit / n_groups;
         const int2 ud = units[DENSE ? unit : unit - unit_part * n_groups];
         const int s = ud.x + lane;
@@ -824,12 +827,14 @@ __device__ __forceinline__ void embed_body(const GridDev& g, const float* __rest
                                            float* __restrict__ eb, int emb_stride, int l_begin, int l_end, int* work) {
     const int lane = threadIdx.x & 31, half = lane & 1;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    int pending = 0;                                   // DYN: lane 0's fetch of the unit after the current one, issued a unit ahead
     auto next_unit = [&](int prev) {
         if (!DYN) return prev + n_warps * 16;
-        int u = 0;
-        if (lane == 0) u = atomicAdd(work, 1);
-        return __shfl_sync(0xffffffffu, u, 0) * 16;
+        const int u = __shfl_sync(0xffffffffu, pending, 0);
+        if (lane == 0) pending = atomicAdd(work, 1);
+        return u * 16;
     };
+    if (DYN && lane == 0) pending = atomicAdd(work, 1);
     const bool fast_mod = g.T_magic40 != 0;
     const unsigned int T32 = (unsigned int)g.T;
     for (int base = DYN ? next_unit(0) : warp * 16; base < n; base = next_unit(base)) {

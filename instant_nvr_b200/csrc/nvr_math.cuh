@@ -409,17 +409,25 @@ NVR_HD bool nvr_cull_quick(const VolumeDev& v, const CullQuick& q, const float* 
     return m > thresh * NVR_CULL_MARGIN;
 }
 
-// k_cull's depth-major walk over the samples of a pass (csrc/nvr_kernels.cuh):
-// position inside the walk -> (ray, step, sample id).  g0 / w0: group index and offset of the CTA's first position
-// (one 64-bit division per 2048 positions); everything per position is 32-bit.
+// k_cull's walk over the samples of a pass (csrc/nvr_kernels.cuh): position inside the walk -> (ray, step, sample id).
+// Rays are taken in groups of 32 and a group is walked in CHUNKS of 32 positions = 16 rays x 2 depth steps, so 32 consecutive
+// positions (one warp iteration, and later one KNN unit / one warp of every other kernel) are a patch ~6 cm x 3 cm instead of
+// a 13 cm x 1.5 cm strip of 32 rays at one depth.  Chunk c of a group: half = (c >> 2) & 1 (rays 0-15 or 16-31 of the group),
+// depth pair = ((c >> 3) << 2) | (c & 3) -- i.e. a warp's 8 chunks are 8 depth steps of one half, then the same 8 steps of the
+// other half, so a lane changes ray once per span.  The pairs are padded to a multiple of 4 (steps >= S are invalid
+// positions), which makes chunk -> (half, pair) a bijection; for S = 64 / 128 / 256 nothing is padded.
+// g0 / w0: group index and offset of the CTA's first position (one 64-bit division per 2048 positions); everything per
+// position is 32-bit.
 struct CullWalk { long long g0; unsigned w0, group; int S; long long n_rays; };
+NVR_HD unsigned cull_group_positions(int S) { return 64u * ((((unsigned)S + 1u) / 2u + 3u) & ~3u); }
 NVR_HD bool cull_locate(const CullWalk& cw, int local, long long& r, int& k, long long& i) {
     const unsigned wl = cw.w0 + (unsigned)local;
     const unsigned q = wl / cw.group, w = wl - q * cw.group;
-    k = (int)(w >> 5);
-    r = (cw.g0 + q) * 32 + (w & 31);
+    const unsigned c = w >> 5, sub = w & 31u;
+    k = (int)(((((c >> 3) << 2) | (c & 3u)) << 1) | (sub >> 4));
+    r = (cw.g0 + q) * 32 + (((c >> 2) & 1u) << 4) + (sub & 15u);
     i = r * cw.S + k;
-    return r < cw.n_rays;
+    return r < cw.n_rays && k < cw.S;
 }
 
 

@@ -294,6 +294,25 @@ class Engine:
         return raw
 
     # ---- training ---------------------------------------------------------------------------------
+    # The forward's workspace (43 MB at 1024 rays x 64) must live until its backward, the backward's scratch only for the call.
+    # Allocating both per step made the caching allocator split and re-merge its big blocks around the 1.14 GB gradient buffer:
+    # the gradient pointer moved every 2-3 steps (optimizer descriptors rebuilt) and now and then a step paid a cudaMalloc.
+    # They are pooled here instead; a forward whose backward never runs just lets its workspace go with its state dict.
+    def _pool_take(self, kind: str, nbytes: int) -> torch.Tensor:
+        pool = self.__dict__.setdefault("_train_pool", {"ws": [], "scratch": []})[kind]
+        stream = _stream_ptr(self.device)
+        for i, (t, s) in enumerate(pool):
+            if t.numel() == nbytes and s == stream:      # exact size: the backward derives the record stride from it
+                pool.pop(i)
+                return t
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def _pool_give(self, kind: str, t: torch.Tensor) -> None:
+        pool = self.__dict__.setdefault("_train_pool", {"ws": [], "scratch": []})[kind]
+        pool.append((t, _stream_ptr(self.device)))
+        if len(pool) > 2:
+            pool.pop(0)
+
     def train_forward(self, wpts: torch.Tensor, viewdir: torch.Tensor, batch: Dict) -> Dict:
         """nvr_train_forward on all points in one pass.  Returns the outputs plus the private workspace the
         backward needs (kept alive by the returned dict)."""
@@ -304,7 +323,7 @@ class Engine:
         st = {"raw": torch.empty(n, 4, dtype=f32, device=dev), "occ": torch.empty(n, dtype=f32, device=dev),
               "x0": torch.empty(n, 5, 3, dtype=f32, device=dev), "resd": torch.empty(n, 5, 3, dtype=f32, device=dev),
               "tocc": torch.empty(n, 5, dtype=f32, device=dev), "rank_of_slot": torch.empty(n, dtype=torch.int32, device=dev),
-              "ws": torch.empty(int(self.lib.nvr_workspace_bytes(self._h, max(n, 64))), dtype=torch.uint8, device=dev),
+              "ws": self._pool_take("ws", int(self.lib.nvr_workspace_bytes(self._h, max(n, 64)))),
               "n": n, "batch": batch}
         self._check(self.lib.nvr_train_forward(self._h, wpts.data_ptr(), viewdir.data_ptr(), n, st["raw"].data_ptr(),
                                                st["occ"].data_ptr(), st["x0"].data_ptr(), st["resd"].data_ptr(),
@@ -317,7 +336,7 @@ class Engine:
         self.bind_params(net)
         self.bind_frame(st["batch"])
         n = st["n"]
-        scratch = torch.empty(int(self.lib.nvr_train_scratch_bytes(self._h, max(n, 64))), dtype=torch.uint8, device=self.device)
+        scratch = self._pool_take("scratch", int(self.lib.nvr_train_scratch_bytes(self._h, max(n, 64))))
         G = _params_struct(net, grads)
         d_raw = _dev_f32(d_raw, self.device)
         d_resd = None if d_resd is None else _dev_f32(d_resd, self.device)      # converted ONCE: the pointers below are theirs
@@ -327,6 +346,9 @@ class Engine:
                                                 st["rank_of_slot"].data_ptr(), n,
                                                 C.byref(G), st["ws"].data_ptr(), st["ws"].numel(), scratch.data_ptr(),
                                                 scratch.numel(), _stream_ptr(self.device)), "nvr_train_backward")
+        # both buffers are dead once the backward's kernels have run; later users are ordered behind them on the same stream
+        self._pool_give("scratch", scratch)
+        self._pool_give("ws", st.pop("ws"))
 
     def deformer_backward(self, tpts: torch.Tensor, d_resd: torch.Tensor, batch: Dict, net, grads: Dict[str, torch.Tensor]) -> None:
         self.bind_params(net)

@@ -130,7 +130,14 @@ class FusedAdam(torch.optim.Optimizer):
             b = e.group["betas"]
             if (b[0], b[1], e.group["eps"]) != e.hyper:
                 return False
-            if (g is None or g.data_ptr() != e.gptr or e.p.data_ptr() != e.pptr or st.get("exp_avg") is not e.m
+            if g is None:
+                return False
+            gp = g.data_ptr()
+            if gp != e.gptr:             # a new gradient buffer (the allocator handed the backward another block): patch the pointer
+                if g.is_sparse or g.dtype != torch.float32 or not g.is_contiguous() or g.device != e.p.device:
+                    return False         # rebuilt -> _build_plan raises the proper error
+                e.a.grad = e.gptr = gp
+            if (e.p.data_ptr() != e.pptr or st.get("exp_avg") is not e.m
                     or st.get("exp_avg_sq") is not e.v or st.get("step") is not e.step_t or self.state.get(e.p) is not st):
                 return False
             seen += 1

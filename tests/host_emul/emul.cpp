@@ -250,7 +250,7 @@ void emul_adam(float* p, const float* g, float* m, float* v, long long n, long l
 void emul_cull_walk(long long n_rays, int S, int grid, int* visits, long long* n_positions) {
     const int SPAN = 2048, T = 8;
     CullWalk cw;
-    cw.S = S; cw.group = 32u * (unsigned)S; cw.n_rays = n_rays;
+    cw.S = S; cw.group = cull_group_positions(S); cw.n_rays = n_rays;
     const long long n_map = ((n_rays + 31) / 32) * (long long)cw.group;
     long long pos = 0;
     for (int block = 0; block < grid; ++block)

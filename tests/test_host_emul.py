@@ -309,7 +309,7 @@ def test_cull_quick_world_space_is_conservative(emul):
 @pytest.mark.parametrize("n_rays,S", [(1, 1), (1, 7), (31, 16), (32, 64), (33, 64), (100, 128), (1000, 3), (4097, 32), (20000, 128),
                                       (65, 256), (7, 1000)])
 def test_cull_walk_visits_every_sample_once(emul, n_rays, S):
-    """k_cull's depth-major walk (groups of 32 rays, 2048-position spans, 8 depth steps per warp) is a bijection onto the
+    """k_cull's depth-major walk (groups of 32 rays in chunks of 16 rays x 2 steps, 2048-position spans) is a bijection onto the
     n_rays x S samples for ragged sizes: ray counts that are not multiples of 32, sample counts that do not divide a span."""
     visits = np.zeros(n_rays * S, dtype=np.int32)
     npos = C.c_longlong(0)
@@ -317,4 +317,5 @@ def test_cull_walk_visits_every_sample_once(emul, n_rays, S):
         visits[:] = 0
         emul.emul_cull_walk(C.c_longlong(n_rays), C.c_int(S), C.c_int(grid), visits.ctypes.data_as(C.c_void_p), C.byref(npos))
         assert visits.min() == 1 and visits.max() == 1, (grid, int(visits.min()), int(visits.max()))
-        assert npos.value >= n_rays * S and npos.value < (n_rays + 32) * S + 2048
+        group = 64 * ((((S + 1) // 2) + 3) // 4 * 4)           # positions per 32 rays: depth pairs padded to a multiple of 4
+        assert npos.value >= n_rays * S and npos.value < ((n_rays + 31) // 32) * group + 2048
