@@ -21,7 +21,7 @@ def _worker(rank, world, port, q):
     from instant_nvr_b200.synthetic import fill_weights, make_frame, make_rays
     cfg = PathConfig.inb_377(N_samples=32, log2_T_cap=14)
     frame = make_frame(seed=2)
-    rays = make_rays(frame, 96, 96)
+    rays = make_rays(frame, 208, 208)      # 1.38 M samples: each rank's shard is >= 2^19 samples, i.e. a two-lane render
     net = Network(cfg, device="cpu")
     fill_weights(net.state_dict(), seed=2, table_gain=100.0, bounds=frame["bounds"][0])
     net = net.cuda().eval()
@@ -39,9 +39,11 @@ def _worker(rank, world, port, q):
     n = o.shape[0]
     idx = shard_indices(n, rank, world, tile=256).cuda()
     pf = PeerFrame(eng, n, rank, world, tile=256)
+    ok = ok and idx.numel() * cfg.N_samples >= 1 << 19
     for it in range(3):
         frame_t, l_rgb, l_acc = pf.render(o[idx], d[idx], nr[idx], fr[idx], cfg.N_samples, want_local=True)
         torch.cuda.synchronize()
+        ok = ok and eng.counters()["n_passes"] == 2     # the compositing kernels of BOTH lanes stored into the peers' frames
         ok = ok and bool(torch.equal(frame_t[:, :3], ref_rgb) and torch.equal(frame_t[:, 3], ref_acc))
         ok = ok and bool(torch.equal(l_rgb, ref_rgb[idx]) and torch.equal(l_acc, ref_acc[idx]))
     frame_t = pf.allgather(ref_rgb[idx].contiguous(), ref_acc[idx].contiguous())
