@@ -51,6 +51,7 @@ struct NvrEngine {
     long long launches = 0;
     long long last_points = 0;
     long long last_passes = 1;
+    long long two_lane_min = 1ll << 19;     // render calls of at least this many samples run as two lanes (NVR_TWO_LANE_MIN_SAMPLES)
     int last_lanes = 1;                     // 2: the most recent call carved its workspace into two halves (two-lane render)
     // multi-GPU frame assembly (nvr_frame.cuh): the local buffer [flags | slot 0 | slot 1] and the peers' mappings
     struct PeerFrame {
@@ -133,6 +134,10 @@ extern "C" int nvr_create(const NvrConfig* cfg, NvrHandle* out) {
     }
     NvrEngine* h = new NvrEngine();
     h->cfg = *cfg;
+    if (const char* e = getenv("NVR_TWO_LANE_MIN_SAMPLES")) {          // tests / sanitizer runs: two lanes on small renders
+        const long long v = atoll(e);
+        if (v >= 128) h->two_lane_min = v;
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
     if (cudaSetDevice(cfg->device) != cudaSuccess || cudaMalloc(&h->d_cl_off, 8 * sizeof(int)) != cudaSuccess ||
@@ -559,12 +564,11 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
     // not depend on which rays share a pass, so the output is bit-identical to the one-lane render.  Not in the serialised
     // profiling mode, not for small calls.
     Workspace lane_w[2];
-    const long long TWO_LANE_MIN_SAMPLES = 1ll << 19;
     const size_t half_bytes = (ws_bytes / 2) & ~(size_t)255;
     const bool two = !h->profiling && !(h->cfg.tune & (NVR_TUNE_SERIAL | NVR_TUNE_ONE_LANE | NVR_TUNE_LEVEL_MAJOR)) &&
-                     n_rays * (long long)n_samples >= TWO_LANE_MIN_SAMPLES &&
+                     n_rays * (long long)n_samples >= h->two_lane_min &&
                      carve(workspace, half_bytes, lane_w[0]) && carve((char*)workspace + half_bytes, half_bytes, lane_w[1]) &&
-                     lane_w[1].pts / n_samples >= 64;
+                     lane_w[1].pts / n_samples >= 1;
     if (two) {
         rays_per_pass = std::min<long long>(lane_w[1].pts / n_samples, (n_rays + 1) / 2);
         NVR_CHECK(h, cudaMemsetAsync(h->d_counters_snapshot, 0, NVR_CTR_WORDS * sizeof(int), st));

@@ -284,6 +284,39 @@ def test_render_host_and_multipass_match(gpu):
 
 
 @pytest.mark.parametrize("gain,thresh", [(1.0, None), (200.0, None), (200.0, 0.1), (200.0, 0.02)])
+def test_two_lane_render_matches_one_lane(gpu, monkeypatch):
+    """A render call of >= 2^19 samples runs as two lanes (two passes on two streams of the engine, half a workspace each); here
+    the threshold is lowered so the small fixture takes that path: same bits as the one-lane render, device and host entry points,
+    the counters are the two passes' sums and the gather footprint is the union over both halves."""
+    from instant_nvr_b200.engine import Engine
+    cfg, net = gpu["cfg"], gpu["nets"][200.0]
+    gb = gpu["gbatch"]
+    S = cfg.N_samples
+    o, d, n, f = gb["ray_o"][0], gb["ray_d"][0], gb["near"][0], gb["far"][0]
+    eng1 = Engine(cfg, tune=2048)                                # NVR_TUNE_ONE_LANE
+    eng1.bind_params(net)
+    rgb1, acc1, raw1 = eng1.render_rays(o, d, n, f, S, batch=gb, want_raw=True)
+    c1, fp1 = eng1.counters(), eng1.gather_footprint()
+    monkeypatch.setenv("NVR_TWO_LANE_MIN_SAMPLES", "1024")
+    eng2 = Engine(cfg)
+    monkeypatch.delenv("NVR_TWO_LANE_MIN_SAMPLES")
+    eng2.bind_params(net)
+    rgb2, acc2, raw2 = eng2.render_rays(o, d, n, f, S, batch=gb, want_raw=True)
+    c2, fp2 = eng2.counters(), eng2.gather_footprint()
+    assert c1["n_passes"] == 1 and c2["n_passes"] == 2
+    assert torch.equal(raw2, raw1) and torch.equal(rgb2, rgb1) and torch.equal(acc2, acc1)
+    assert c2["n_survivors"] == c1["n_survivors"] and c2["n_far_pairs"] == c1["n_far_pairs"] and fp2 == fp1
+    assert [a - 2 for a in c2["n_pairs"]] == [a - 1 for a in c1["n_pairs"]]
+    host = [t.cpu().contiguous().pin_memory() for t in (o, d, n, f)]
+    rgb_h, acc_h = torch.empty(o.shape[0], 3).pin_memory(), torch.empty(o.shape[0]).pin_memory()
+    eng2.render_rays_host(*host, S, rgb_h, acc_h)
+    assert torch.equal(rgb_h, rgb1.cpu()) and torch.equal(acc_h, acc1.cpu())
+    # odd ray counts: the second lane takes the shorter half, a single ray stays one pass
+    for k in (1, 2, 3, 65):
+        a, b = eng2.render_rays(o[:k], d[:k], n[:k], f[:k], S)
+        assert torch.equal(a, rgb1[:k]) and torch.equal(b, acc1[:k])
+
+
 def test_far_field_pairs_share_one_evaluation(gpu, gain, thresh):
     """Default mode answers every flagged pair whose Gaussian weights sum to < 1e-20 (part farther than ~0.73 m) with ONE
     shared zero-weight evaluation per part (csrc/nvr_kernels.cuh NVR_FAR_WSUM); NVR_TUNE_NO_FAR_COLLAPSE evaluates each

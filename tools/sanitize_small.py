@@ -35,6 +35,20 @@ pf = PeerFrame(eng, o.shape[0], 0, 1, tile=64)
 fr = pf.render(o, d, n, f, 16)
 assert torch.equal(fr[:, :3], rgb)
 pf.close()
+# the same frame as a two-lane render (two passes on two engine streams, half a workspace each), device and host entry points
+os.environ["NVR_TWO_LANE_MIN_SAMPLES"] = "1024"
+from instant_nvr_b200.engine import Engine
+eng2 = Engine(cfg)
+del os.environ["NVR_TWO_LANE_MIN_SAMPLES"]
+eng2.bind_params(net)
+rgb4, acc4, raw4 = eng2.render_rays(o, d, n, f, 16, batch=gb, want_raw=True)
+assert eng2.counters()["n_passes"] == 2 and torch.equal(rgb4, rgb) and torch.equal(raw4, raw)
+print("two-lane footprint", eng2.gather_footprint())
+host = [t.cpu().contiguous().pin_memory() for t in (o, d, n, f)]
+rgb_h, acc_h = torch.empty(o.shape[0], 3).pin_memory(), torch.empty(o.shape[0]).pin_memory()
+eng2.render_rays_host(*host, 16, rgb_h, acc_h)
+assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(acc_h, acc.cpu())
+del eng2
 print("footprint", eng.gather_footprint() if eng._ws is not None and eng.render_rays(o, d, n, f, 16) is not None else None)
 net.train()
 params = [p for p in net.parameters() if p.requires_grad]
