@@ -283,7 +283,6 @@ def test_render_host_and_multipass_match(gpu):
     diag("counters_last_pass", **{k: v for k, v in c.items()})
 
 
-@pytest.mark.parametrize("gain,thresh", [(1.0, None), (200.0, None), (200.0, 0.1), (200.0, 0.02)])
 def test_two_lane_render_matches_one_lane(gpu, monkeypatch):
     """A render call of >= 2^19 samples runs as two lanes (two passes on two streams of the engine, half a workspace each); here
     the threshold is lowered so the small fixture takes that path: same bits as the one-lane render, device and host entry points,
@@ -317,6 +316,7 @@ def test_two_lane_render_matches_one_lane(gpu, monkeypatch):
         assert torch.equal(a, rgb1[:k]) and torch.equal(b, acc1[:k])
 
 
+@pytest.mark.parametrize("gain,thresh", [(1.0, None), (200.0, None), (200.0, 0.1), (200.0, 0.02)])
 def test_far_field_pairs_share_one_evaluation(gpu, gain, thresh):
     """Default mode answers every flagged pair whose Gaussian weights sum to < 1e-20 (part farther than ~0.73 m) with ONE
     shared zero-weight evaluation per part (csrc/nvr_kernels.cuh NVR_FAR_WSUM); NVR_TUNE_NO_FAR_COLLAPSE evaluates each
