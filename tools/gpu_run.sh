@@ -1,7 +1,7 @@
 #!/bin/bash
 # One parametrised GPU-box script (replaces the 17 single-purpose tools/gpu_run_*.sh of round 1).
 #   gpurun --timeout 1500 -- 'bash tools/gpu_run.sh tests smoke bench ref ncu_list ncu_full train'
-# stages:  tests | smoke | bench | ref | refgpu | ncu_list | ncu_full | ncu_src:<kernel-regex> | train | ab:<tune>[,<tune>...]
+# stages:  tests | smoke | bench | ref | refgpu | ncu_list | ncu_full | ncu_src:<kernel-regex> | train | san | ab:<tune>[,<tune>...]
 #          | multi:<N>  (pytest tests/test_gpu_multi.py + torchrun bench at N ranks)   | cfg:<c4|c5>
 set -x
 mkdir -p gpurun_out
@@ -31,6 +31,10 @@ case "$stage" in
     k="${stage#ncu_src:}"
     timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$k" -c 6 -o "gpurun_out/prof_$k" -f \
         python bench.py --steps 1 --warmup 3 --steps-only > "gpurun_out/ncu_$k.log" 2>&1; tail -2 "gpurun_out/ncu_$k.log" ;;
+  san)
+    for tool in memcheck synccheck; do
+      timeout 420 compute-sanitizer --tool $tool python tools/sanitize_small.py > gpurun_out/sanitizer_$tool.txt 2>&1; echo "sanitizer $tool rc=$?"; tail -2 gpurun_out/sanitizer_$tool.txt
+    done ;;
   train)
     timeout 300 python tools/train_breakdown.py > gpurun_out/train_breakdown.log 2>&1; head -9 gpurun_out/train_breakdown.log ;;
   ab:*)
