@@ -457,12 +457,12 @@ class Workload:
             eng.render_rays_host(host["ray_o"], host["ray_d"], host["near"], host["far"], self.cfgd["S"], self.rgb_h, self.acc_h)
         else:
             # every rank: its own tiles in from pinned host memory, the frame assembled on every GPU, its own tiles back out
+            if self.pf is not None:              # one library call: copies on the lanes' streams, render, flag barrier, sync
+                self.pf.render_host(host["ray_o"], host["ray_d"], host["near"], host["far"], self.cfgd["S"], self.rgb_h, self.acc_h)
+                return
             d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
-            if self.pf is not None:
-                _, rgb, acc = self.pf.render(d["ray_o"], d["ray_d"], d["near"], d["far"], self.cfgd["S"], want_local=True)
-            else:
-                rgb, acc = eng.render_rays(d["ray_o"], d["ray_d"], d["near"], d["far"], self.cfgd["S"])
-                assemble(torch.cat([rgb, acc[:, None]], 1), self.n_total, self.rank, self.world)
+            rgb, acc = eng.render_rays(d["ray_o"], d["ray_d"], d["near"], d["far"], self.cfgd["S"])
+            assemble(torch.cat([rgb, acc[:, None]], 1), self.n_total, self.rank, self.world)
             self.rgb_h.copy_(rgb, non_blocking=True)
             self.acc_h.copy_(acc, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -791,7 +791,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "ray-samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": wl.n_local * 32 * world, "d2h_bytes_per_step": wl.n_local * 16 * world,
                     "api": "nvr_render_rays_host (pinned host rays -> H2D -> render -> D2H rgb/acc)" if world == 1 else
-                           "per rank: pinned host rays of its tiles -> H2D -> render -> frame assembled on every GPU -> D2H of its tiles"},
+                           "per rank: nvr_render_rays_frame_host (pinned host rays of its tiles -> H2D -> render -> frame assembled on every GPU -> D2H of its tiles)"},
             "gpu_launches": launches,
             "clocks": clocks, "clocks_e2e": clocks_e2e,
             "roofline": roofline,

@@ -211,6 +211,14 @@ int nvr_render_rays_frame(NvrHandle h, const float* ray_o, const float* ray_d, c
                           void* workspace, size_t ws_bytes, void* stream, const float** frame_out);
 int nvr_allgather_frame(NvrHandle h, const float* rgb_map, const float* acc_map, int64_t n_rays_local, void* stream,
                         const float** frame_out);
+/* nvr_render_rays_frame with HOST ray buffers of this rank's shard and HOST outputs for the shard's own pixels (pinned memory
+ * recommended), like nvr_render_rays_host: the copies ride on the lanes' streams (the second lane's rays arrive under the first
+ * lane's kernels, the first lane's pixels leave under the second's), then the flag barrier and a synchronise of `stream`.
+ * `dev_io`: device scratch of at least n_rays_local * 48 bytes. */
+int nvr_render_rays_frame_host(NvrHandle h, const float* ray_o_host, const float* ray_d_host, const float* near_host,
+                               const float* far_host, int64_t n_rays_local, int32_t n_samples, float* rgb_map_host,
+                               float* acc_map_host, void* dev_io, void* workspace, size_t ws_bytes, void* stream,
+                               const float** frame_out);
 
 /* == Network.resd (inb_part_network_multiassign.py:122-124; uv_deformer.py:23-45, flag=None) ==
  * canonical points (n,3) -> 0.05*tanh(MLP(grid(u,v,t))) (n,3). */

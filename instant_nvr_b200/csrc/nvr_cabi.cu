@@ -52,7 +52,8 @@ struct NvrEngine {
     long long last_points = 0;
     long long last_passes = 1;
     long long two_lane_min = 1ll << 19;     // render calls of at least this many samples run as two lanes (NVR_TWO_LANE_MIN_SAMPLES)
-    int last_lanes = 1;                     // 2: the most recent call carved its workspace into two halves (two-lane render)
+    int last_lanes = 1;
+    int last_lanes_used = 1;                // how many of the two half workspaces a pass ran in (a one-ray call: only the first)                     // 2: the most recent call carved its workspace into two halves (two-lane render)
     // multi-GPU frame assembly (nvr_frame.cuh): the local buffer [flags | slot 0 | slot 1] and the peers' mappings
     struct PeerFrame {
         void* local = nullptr; void* peer[NVR_MAX_RANKS] = {nullptr};
@@ -494,6 +495,7 @@ static int run_pass(NvrEngine* h, const Workspace& w, const float* pts, const fl
     h->last_points = n;
     h->last_passes = 1;
     h->last_lanes = 1;
+    h->last_lanes_used = 1;
     return 0;
 }
 
@@ -613,6 +615,7 @@ static int render_rays_impl(NvrHandle h, const float* ray_o, const float* ray_d,
         h->last_points = n_rays * (long long)n_samples;
         h->last_passes = pass;
         h->last_lanes = 2;
+        h->last_lanes_used = pass >= 2 ? 2 : 1;
         return rc;
     }
     if (hio) {
@@ -747,6 +750,27 @@ extern "C" int nvr_render_rays_frame(NvrHandle h, const float* ray_o, const floa
     if (int rc = render_rays_impl(h, ray_o, ray_d, near_, far_, n_rays_local, n_samples, rgb_map, acc_map, nullptr, workspace, ws_bytes, stream_, fo))
         return rc;
     return frame_finish(h, fo, (cudaStream_t)stream_, frame_out);
+}
+
+extern "C" int nvr_render_rays_frame_host(NvrHandle h, const float* ray_o_host, const float* ray_d_host, const float* near_host,
+                                          const float* far_host, int64_t n_rays, int32_t n_samples, float* rgb_map_host,
+                                          float* acc_map_host, void* dev_io, void* workspace, size_t ws_bytes, void* stream_,
+                                          const float** frame_out) {
+    if (!h) return 1;
+    if (!h->pf.connected) return fail(h, "nvr_render_rays_frame_host: nvr_frame_create + nvr_frame_connect first");
+    if (n_rays > 0 && (!dev_io || !ray_o_host || !ray_d_host || !near_host || !far_host || !rgb_map_host || !acc_map_host))
+        return fail(h, "nvr_render_rays_frame_host: null argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    float* d = (float*)dev_io;                      // [o 3n | d 3n | near n | far n | rgb 3n | acc n] = 12n floats
+    float *d_o = d, *d_d = d + 3 * n_rays, *d_n = d + 6 * n_rays, *d_f = d + 7 * n_rays, *d_rgb = d + 8 * n_rays,
+          *d_acc = d + 11 * n_rays;
+    const HostIO hio{ray_o_host, ray_d_host, near_host, far_host, rgb_map_host, acc_map_host};
+    const FrameOut fo = frame_next(h);
+    if (int rc = render_rays_impl(h, d_o, d_d, d_n, d_f, n_rays, n_samples, d_rgb, d_acc, nullptr, workspace, ws_bytes, stream_, fo, &hio))
+        return rc;
+    if (int rc = frame_finish(h, fo, st, frame_out)) return rc;
+    NVR_CHECK(h, cudaStreamSynchronize(st));
+    return 0;
 }
 
 extern "C" int nvr_allgather_frame(NvrHandle h, const float* rgb_map, const float* acc_map, int64_t n_rays_local, void* stream_,
@@ -1278,7 +1302,7 @@ extern "C" int nvr_gather_footprint(NvrHandle h, void* workspace, size_t ws_byte
         const NvrGrid& g = h->params.part[p].grid;
         const size_t words = (size_t)((2 * (dense_rows(g) + hash_rows(g)) + 31) / 32);
         cudaMemsetAsync(bitmap, 0, words * sizeof(unsigned int), st);
-        for (int l = 0; l < lanes; ++l) {
+        for (int l = 0; l < h->last_lanes_used; ++l) {
             const Workspace& w = lw[l];
             k_embed_footprint<<<h->sm_count * 8, 256, 0, st>>>(h->part_grid[p], (const float*)(w.pairs + (long long)p * w.cap), 8,
                                                                w.counters + NVR_CTR_PAIR + p, bitmap, 2ull * (unsigned long long)dense_rows(g));

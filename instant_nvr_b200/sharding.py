@@ -122,6 +122,27 @@ class PeerFrame:
         frame = self._view(out.value)
         return (frame, rgb, acc) if want_local else frame
 
+    def render_host(self, ray_o, ray_d, near, far, n_samples: int, rgb_out, acc_out, batch=None) -> torch.Tensor:
+        """``render`` with this rank's shard in HOST (pinned) buffers and its own pixels delivered to host buffers; the copies
+        ride on the render's two lanes.  Returns the assembled frame (device); the call has synchronised the stream."""
+        from .engine import _stream_ptr
+        eng = self.eng
+        if batch is not None:
+            eng.bind_frame(batch)
+        eng._refresh_inference_tables()
+        for t in (ray_o, ray_d, near, far, rgb_out, acc_out):
+            if t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("render_host takes contiguous fp32 CPU tensors")
+        R = ray_o.shape[0]
+        if eng._io is None or eng._io.numel() < 12 * R:
+            eng._io = torch.empty(max(12 * R, 12), dtype=torch.float32, device=eng.device)
+        ws, ws_bytes = eng._workspace(R * n_samples)
+        out = C.c_void_p()
+        eng._check(eng.lib.nvr_render_rays_frame_host(eng._h, ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(), far.data_ptr(), R,
+                                                      int(n_samples), rgb_out.data_ptr(), acc_out.data_ptr(), eng._io.data_ptr(),
+                                                      ws, ws_bytes, _stream_ptr(eng.device), C.byref(out)), "nvr_render_rays_frame_host")
+        return self._view(out.value)
+
     def allgather(self, rgb: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
         """Unfused form: scatter already rendered shard pixels + barrier."""
         from .engine import _dev_f32, _stream_ptr

@@ -46,6 +46,13 @@ def _worker(rank, world, port, q):
         ok = ok and eng.counters()["n_passes"] == 2     # the compositing kernels of BOTH lanes stored into the peers' frames
         ok = ok and bool(torch.equal(frame_t[:, :3], ref_rgb) and torch.equal(frame_t[:, 3], ref_acc))
         ok = ok and bool(torch.equal(l_rgb, ref_rgb[idx]) and torch.equal(l_acc, ref_acc[idx]))
+    # host-buffer form (nvr_render_rays_frame_host): the shard's rays come from pinned memory on the lanes' streams, its own
+    # pixels go back the same way
+    hr = [t[idx].cpu().contiguous().pin_memory() for t in (o, d, nr, fr)]
+    h_rgb, h_acc = torch.empty(idx.numel(), 3).pin_memory(), torch.empty(idx.numel()).pin_memory()
+    frame_t = pf.render_host(*hr, cfg.N_samples, h_rgb, h_acc)
+    ok = ok and bool(torch.equal(frame_t[:, :3], ref_rgb) and torch.equal(frame_t[:, 3], ref_acc))
+    ok = ok and bool(torch.equal(h_rgb, ref_rgb[idx].cpu()) and torch.equal(h_acc, ref_acc[idx].cpu()))
     frame_t = pf.allgather(ref_rgb[idx].contiguous(), ref_acc[idx].contiguous())
     torch.cuda.synchronize()
     ok = ok and bool(torch.equal(frame_t[:, :3], ref_rgb) and torch.equal(frame_t[:, 3], ref_acc))

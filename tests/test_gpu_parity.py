@@ -671,6 +671,12 @@ def test_peer_frame_single_rank(gpu):
             eng._ws = None
         g = pf.allgather(rgb, acc)
         assert torch.equal(g[:, :3], rgb) and torch.equal(g[:, 3], acc)
+        # host-buffer form (nvr_render_rays_frame_host)
+        host = [t.cpu().contiguous().pin_memory() for t in (o, d, n, f)]
+        rgb_h, acc_h = torch.empty(R, 3).pin_memory(), torch.empty(R).pin_memory()
+        fourth = pf.render_host(*host, S, rgb_h, acc_h)
+        assert torch.equal(fourth[:, :3], rgb) and torch.equal(fourth[:, 3], acc)
+        assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(acc_h, acc.cpu())
     finally:
         pf.close()
 
