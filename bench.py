@@ -399,6 +399,48 @@ def train_step_report(net, gframe, frame, n_rays=1024, n_samples=64, steps=10):
         net.cfg = cfg0
 
 
+def grad_allreduce_check(rank, world):
+    """tests/test_gpu_multi.py::test_two_rank_gradient_allreduce_equals_full_batch inside the multi-GPU bench run (the driver's
+    GPU test box has one GPU and skips it): every rank back-propagates its 1/world of the rays of one small training batch, the
+    gradients are all-reduced over NCCL and compared with the single-GPU gradient of the whole batch (the loss is a sum over
+    rays) -- what the reference's DDP wrapper relies on."""
+    import torch.distributed as dist
+    from instant_nvr_b200.config import PathConfig
+    from instant_nvr_b200.network import Network
+    from instant_nvr_b200.renderer import Renderer
+    from instant_nvr_b200.synthetic import fill_weights, make_frame, make_rays
+    cfg = PathConfig.inb_377(N_samples=16, log2_T_cap=12).with_(use_pair_reg=False)
+    frame = make_frame(seed=5)
+    rays = make_rays(frame, 24, 24)
+    net = Network(cfg, device="cpu")
+    fill_weights(net.state_dict(), seed=5, table_gain=100.0, bounds=frame["bounds"][0])
+    net = net.cuda().train()
+    gb = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in {**frame, **rays}.items()}
+    R = gb["ray_o"].shape[1]
+    tgt = torch.rand(1, R, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    r = Renderer(net)
+
+    def grads_for(sel):
+        for p in net.parameters():
+            p.grad = None
+        b = dict(gb)
+        for k in ("ray_o", "ray_d", "near", "far", "occupancy"):
+            b[k] = gb[k][:, sel]
+        ret = r.render(b)
+        (((ret["rgb_map"] - tgt[:, sel]) ** 2).sum() + ret["resd"].pow(2).sum()).backward()
+        return {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in net.named_parameters() if p.requires_grad}
+    full = grads_for(torch.arange(R, device="cuda"))
+    mine = grads_for(torch.arange(rank, R, world, device="cuda"))
+    worst = torch.zeros(1, device="cuda")
+    for n, g in mine.items():
+        dist.all_reduce(g)
+        worst = torch.maximum(worst, (g - full[n]).abs().max() / (full[n].abs().max() + 1e-12))
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    w = float(worst.item())
+    return {"worst_relative_difference": w, "tensors": len(mine), "rays": int(R), "ok": w < 1e-3,
+            "what": "all-reduced per-rank gradients (each rank: 1/world of the rays) vs the single-GPU gradient of the whole batch"}
+
+
 def cpu_state_dict(S, seed=0):
     from instant_nvr_b200.config import PathConfig
     from instant_nvr_b200.network import Network
@@ -690,6 +732,12 @@ def main():
                            "max_abs_diff_rank0": float((assembled[:, :4] - ref).abs().max().item()), "rays": wl.n_total}
         except Exception as ex:
             frame_check = {"error": f"{type(ex).__name__}: {ex}"}
+    grad_check = None
+    if world > 1 and not args.no_extras:
+        try:
+            grad_check = grad_allreduce_check(rank, world)
+        except Exception as ex:
+            grad_check = {"error": f"{type(ex).__name__}: {ex}"}
     extras = {}
     wl.close()                                       # one peer frame buffer per engine: the supplementary workloads bring their own
     if not args.no_extras:
@@ -803,7 +851,7 @@ def main():
                           f"({ms_prof / p_steps:.3f} ms/step in that mode); the headline steps run without the events",
             "embed_part_ms": [per(v) for v in prof["embed_part_ms"]], "mlp_part_ms": [per(v) for v in prof["mlp_part_ms"]],
             "csrc_hash": csrc_hash(),
-            "frame_check": frame_check,
+            "frame_check": frame_check, "grad_allreduce_check": grad_check,
             "cpu_baseline": extras.pop("cpu_baseline", None),
         }
         line.update(extras)
