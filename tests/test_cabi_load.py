@@ -68,3 +68,45 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "nvr_oracle" not in text and "import oracle" not in text, os.path.join(root, f)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in instant_nvr_b200/cabi.py against the C compiler's view of include/nvr_b200.h: sizeof every struct
+    and offsetof every field (a drifted mirror would pass garbage pointers across the boundary without any error)."""
+    import subprocess
+    from instant_nvr_b200 import cabi
+    header = open(os.path.join(REPO, "include", "nvr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    structs = {}
+    for m in re.finditer(r"typedef struct (Nvr\w+)\s*\{(.*?)\}\s*\1\s*;", text, flags=re.S):
+        name, body = m.group(1), m.group(2)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):                      # `int64_t a, b;` style declarations
+                fm = re.search(r"(\w+)\s*(\[[^\]]*\]\s*)*$", part.strip())
+                assert fm, (name, decl)
+                fields.append(fm.group(1))
+        structs[name] = fields
+    assert len(structs) >= 12 and len(structs["NvrFrame"]) >= 15 and "n_passes" in structs["NvrCounters"]
+    mirrors = {n: getattr(cabi, n) for n in structs if hasattr(cabi, n)}
+    assert set(mirrors) == set(structs), sorted(set(structs) - set(mirrors))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nvr_b200.h"', 'int main(void) {']
+    for name, fields in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for f in fields:
+            lines.append(f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), "-o", str(exe), str(src)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, fields in structs.items():
+        cls = mirrors[name]
+        assert int(out[name]) == C.sizeof(cls), (name, out[name], C.sizeof(cls))
+        assert [f for f, *_ in cls._fields_] == fields, (name, [f for f, *_ in cls._fields_], fields)
+        for f in fields:
+            assert int(out[f"{name}.{f}"]) == getattr(cls, f).offset, (name, f)
