@@ -269,6 +269,28 @@ void emul_cull_walk(long long n_rays, int S, int grid, int* visits, long long* n
         }
     *n_positions = pos;
 }
+// extent of every aligned 32-position chunk of the walk (= one warp iteration of k_cull, the granule of the survivor order):
+// the largest number of distinct rays and of distinct depth steps a chunk covers, over the whole walk
+void emul_cull_chunk_extent(long long n_rays, int S, int* max_rays, int* max_steps) {
+    CullWalk cw;
+    cw.S = S; cw.group = cull_group_positions(S); cw.n_rays = n_rays;
+    const long long n_map = ((n_rays + 31) / 32) * (long long)cw.group;
+    *max_rays = 0; *max_steps = 0;
+    for (long long sbase = 0; sbase < n_map; sbase += 32) {
+        cw.g0 = sbase / (long long)cw.group;
+        cw.w0 = (unsigned)(sbase - cw.g0 * (long long)cw.group);
+        long long rlo = 1ll << 60, rhi = -1; int klo = 1 << 30, khi = -1;
+        for (int lane = 0; lane < 32; ++lane) {
+            long long r, i; int k;
+            if (!cull_locate(cw, lane, r, k, i)) continue;
+            rlo = r < rlo ? r : rlo; rhi = r > rhi ? r : rhi; klo = k < klo ? k : klo; khi = k > khi ? k : khi;
+        }
+        if (rhi >= 0) {
+            if ((int)(rhi - rlo + 1) > *max_rays) *max_rays = (int)(rhi - rlo + 1);
+            if (khi - klo + 1 > *max_steps) *max_steps = khi - klo + 1;
+        }
+    }
+}
 // quick world-space cull (nvr_cull_quick) next to the exact decision for world points: keep = exact lookup < thresh
 void emul_cull_quick(const float* dist, int D, int H, int W, const float* bounds, const float* R, const float* Th, const float* wpts,
                      long long n, float thresh, unsigned char* keep, unsigned char* quick) {

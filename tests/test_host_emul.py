@@ -319,3 +319,12 @@ def test_cull_walk_visits_every_sample_once(emul, n_rays, S):
         assert visits.min() == 1 and visits.max() == 1, (grid, int(visits.min()), int(visits.max()))
         group = 64 * ((((S + 1) // 2) + 3) // 4 * 4)           # positions per 32 rays: depth pairs padded to a multiple of 4
         assert npos.value >= n_rays * S and npos.value < ((n_rays + 31) // 32) * group + 2048
+
+
+@pytest.mark.parametrize("n_rays,S", [(32, 64), (100, 128), (4097, 32), (65, 256), (33, 7)])
+def test_cull_walk_chunks_are_compact(emul, n_rays, S):
+    """32 consecutive positions of the walk -- one warp iteration of k_cull, hence the granule of the survivor order and of the
+    KNN units -- cover at most 16 consecutive rays and 2 consecutive depth steps (csrc/nvr_math.cuh cull_locate)."""
+    mr, ms = C.c_int(0), C.c_int(0)
+    emul.emul_cull_chunk_extent(C.c_longlong(n_rays), C.c_int(S), C.byref(mr), C.byref(ms))
+    assert 1 <= mr.value <= 16 and 1 <= ms.value <= 2, (mr.value, ms.value)
