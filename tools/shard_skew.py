@@ -53,7 +53,7 @@ def main():
             step()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps, c["n_survivors"], sum(c["n_pairs"]) - sum(c["n_far_pairs"])
+        return e0.elapsed_time(e1) / steps, c["n_survivors"], sum(c["n_pairs"])      # n_pairs = pairs EVALUATED (far-field pairs are separate)
 
     full_ms, full_surv, full_pairs = time_shard(torch.arange(n, device="cuda"))
     out.write(json.dumps({"world": 1, "rays": n, "ms": full_ms, "survivors": full_surv, "evaluated_pairs": full_pairs}) + "\n")
